@@ -1,0 +1,101 @@
+// Shared helpers for the dvdgan_b200 CUDA library (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/dvdgan_b200.h"
+
+namespace dvd {
+
+extern thread_local char g_last_error[512];
+
+inline int fail(const char* fmt, const char* a = "", const char* file = "", int line = 0) {
+  snprintf(g_last_error, sizeof(g_last_error), fmt, a, file, line);
+  return 1;
+}
+
+#define DVD_CHECK_ARG(cond)                                                          \
+  do {                                                                               \
+    if (!(cond)) return ::dvd::fail("invalid argument: %s (%s:%d)", #cond, __FILE__, __LINE__); \
+  } while (0)
+
+#define DVD_CUDA(expr)                                                               \
+  do {                                                                               \
+    cudaError_t _e = (expr);                                                         \
+    if (_e != cudaSuccess)                                                           \
+      return ::dvd::fail("CUDA error: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+#define DVD_LAUNCH_CHECK()                                                           \
+  do {                                                                               \
+    cudaError_t _e = cudaGetLastError();                                             \
+    if (_e != cudaSuccess)                                                           \
+      return ::dvd::fail("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+#define DVD_TRY(expr)            \
+  do {                           \
+    int _r = (expr);             \
+    if (_r != 0) return _r;      \
+  } while (0)
+
+inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+inline int num_sms() {
+  static thread_local int cached_dev = -1;
+  static thread_local int cached = 148;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (dev != cached_dev) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) cached = n;
+    cached_dev = dev;
+  }
+  return cached;
+}
+
+template <typename T>
+__host__ __device__ inline T ceil_div(T a, T b) { return (a + b - 1) / b; }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Block-wide sum (blockDim.x multiple of 32, <= 1024). Result valid in every thread.
+template <typename T>
+__device__ __forceinline__ T block_sum(T v, T* smem /* >= 32 */) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) smem[wid] = v;
+  __syncthreads();
+  T r = (lane < nw) ? smem[lane] : T(0);
+  r = warp_sum(r);
+  return r;
+}
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+
+// Elementwise launch geometry: a multiple of the SM count, grid-stride loops inside.
+inline int ew_blocks(int64_t n, int per_thread = 4, int threads = 256) {
+  int64_t want = ceil_div<int64_t>(n, (int64_t)per_thread * threads);
+  int64_t cap = (int64_t)num_sms() * 8;
+  if (want < 1) want = 1;
+  return (int)(want < cap ? want : cap);
+}
+
+}  // namespace dvd

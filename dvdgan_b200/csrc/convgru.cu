@@ -1,0 +1,277 @@
+// ConvGRU layer over a whole clip (ConvGRU.py:29-54 driven by Generator.py:87-97), forward and BPTT.
+//
+// conv(cat[x,h]) = conv_x(x) + conv_h(h): the x-halves of all three gates are one batched implicit GEMM over
+// all T frames (Cout = 3*Ch, bias folded in); only the h-halves are sequential in time.  Gates live in one
+// (B,T,3Ch,H,W) buffer = (update, reset, out) that is activated in place and, in the backward sweep,
+// overwritten in place with the pre-activation gradients, which then feed ONE batched x-dgrad and the batched
+// weight gradients.
+#include "common.cuh"
+
+namespace dvd {
+
+// u = sigmoid(gu), r = sigmoid(gr) in place; rh = r * h_prev
+__global__ void gru_gate_ur_kernel(float* __restrict__ g_t, int64_t g_bs, const float* __restrict__ hp, int64_t hp_bs,
+                                   float* __restrict__ rh_t, int64_t rh_bs, int B, int64_t chw) {
+  const int64_t total = (int64_t)B * chw;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int b = (int)(i / chw);
+    const int64_t r = i - (int64_t)b * chw;
+    float* g = g_t + b * g_bs;
+    const float u = sigmoidf_(g[r]);
+    const float rr = sigmoidf_(g[chw + r]);
+    g[r] = u;
+    g[chw + r] = rr;
+    const float h = hp ? hp[b * hp_bs + r] : 0.f;
+    rh_t[b * rh_bs + r] = rr * h;
+  }
+}
+
+// o = tanh(go) in place; h = h_prev * (1 - u) + o * u
+__global__ void gru_out_kernel(float* __restrict__ g_t, int64_t g_bs, const float* __restrict__ hp, int64_t hp_bs,
+                               float* __restrict__ h_t, int64_t h_bs, int B, int64_t chw) {
+  const int64_t total = (int64_t)B * chw;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int b = (int)(i / chw);
+    const int64_t r = i - (int64_t)b * chw;
+    float* g = g_t + b * g_bs;
+    const float u = g[r];
+    const float o = tanhf(g[2 * chw + r]);
+    g[2 * chw + r] = o;
+    const float h = hp ? hp[b * hp_bs + r] : 0.f;
+    h_t[b * h_bs + r] = h * (1.f - u) + o * u;
+  }
+}
+
+// backward, part 1: dhn = dh_ext + carry_in;  da_u -> u slot, da_o -> o slot, carry_out = dhn * (1 - u)
+__global__ void gru_bwd1_kernel(float* __restrict__ g_t, int64_t g_bs, const float* __restrict__ hp, int64_t hp_bs,
+                                const float* __restrict__ dh_t, int64_t dh_bs, const float* __restrict__ carry_in,
+                                float* __restrict__ carry_out, int B, int64_t chw) {
+  const int64_t total = (int64_t)B * chw;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int b = (int)(i / chw);
+    const int64_t r = i - (int64_t)b * chw;
+    float* g = g_t + b * g_bs;
+    const float u = g[r], o = g[2 * chw + r];
+    const float h = hp ? hp[b * hp_bs + r] : 0.f;
+    float dhn = dh_t[b * dh_bs + r];
+    if (carry_in) dhn += carry_in[i];
+    const float du = dhn * (o - h);
+    const float d_o = dhn * u;
+    g[2 * chw + r] = d_o * (1.f - o * o);
+    g[r] = du * u * (1.f - u);
+    carry_out[i] = dhn * (1.f - u);
+  }
+}
+
+// backward, part 2: dr = d_rh * h_prev; carry_out += d_rh * r; da_r -> r slot
+__global__ void gru_bwd2_kernel(float* __restrict__ g_t, int64_t g_bs, const float* __restrict__ hp, int64_t hp_bs,
+                                const float* __restrict__ d_rh, float* __restrict__ carry_out, int B, int64_t chw) {
+  const int64_t total = (int64_t)B * chw;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int b = (int)(i / chw);
+    const int64_t r = i - (int64_t)b * chw;
+    float* g = g_t + b * g_bs;
+    if (!hp) {          // zero previous state: no gradient reaches the reset gate
+      g[chw + r] = 0.f;
+      continue;
+    }
+    const float rr = g[chw + r];
+    const float h = hp[b * hp_bs + r];
+    const float drh = d_rh[i];
+    carry_out[i] += drh * rr;
+    g[chw + r] = drh * h * rr * (1.f - rr);
+  }
+}
+
+struct GruWs {
+  float *wx, *whur, *who, *bias;        // forward operands
+  float *wxT, *whurT, *whoT;            // dgrad operands
+  float *dwx, *dwhur, *dwho;            // packed weight grads
+  float *d_rh, *carry0, *carry1, *dbias;
+  double* dscratch;
+  size_t bytes;
+};
+
+static GruWs carve(void* base, int B, int Cx, int Ch, int HW, int taps, bool bwd) {
+  GruWs w;
+  char* p = reinterpret_cast<char*>(base);
+  size_t off = 0;
+  auto take = [&](size_t n_floats) {
+    float* r = reinterpret_cast<float*>(p + off);
+    off += ((n_floats * sizeof(float) + 255) / 256) * 256;
+    return r;
+  };
+  const size_t nx = (size_t)taps * Cx * 3 * Ch, nur = (size_t)taps * Ch * 2 * Ch, no = (size_t)taps * Ch * Ch;
+  w.wx = take(nx); w.whur = take(nur); w.who = take(no); w.bias = take(3 * Ch);
+  if (bwd) {
+    w.wxT = take(nx); w.whurT = take(nur); w.whoT = take(no);
+    w.dwx = take(nx); w.dwhur = take(nur); w.dwho = take(no);
+    const size_t st = (size_t)B * Ch * HW;
+    w.d_rh = take(st); w.carry0 = take(st); w.carry1 = take(st); w.dbias = take(3 * Ch);
+    w.dscratch = reinterpret_cast<double*>(take(2 * 3 * Ch));
+  } else {
+    w.wxT = w.whurT = w.whoT = w.dwx = w.dwhur = w.dwho = w.d_rh = w.carry0 = w.carry1 = w.dbias = nullptr;
+    w.dscratch = nullptr;
+  }
+  w.bytes = off;
+  return w;
+}
+
+static dvd_conv_desc base_desc(int B, int T, int Cin, int Cout, int H, int W, int k) {
+  dvd_conv_desc d;
+  memset(&d, 0, sizeof(d));
+  d.N1 = B; d.N2 = T; d.Cin = Cin; d.Cout = Cout; d.D = 1; d.H = H; d.W = W; d.kD = 1; d.kH = k; d.kW = k;
+  d.x_cs = d.y_cs = d.r_cs = (int64_t)H * W;
+  return d;
+}
+
+}  // namespace dvd
+
+using namespace dvd;
+
+extern "C" size_t dvd_convgru_layer_workspace_bytes(int B, int T, int Cx, int Ch, int H, int W, int k) {
+  (void)T;
+  return carve(nullptr, B, Cx, Ch, H * W, k * k, true).bytes + 256;
+}
+
+extern "C" int dvd_convgru_layer_fwd(const float* x, int64_t x_bs, int64_t x_ts, const float* h0, const float* wu,
+                                     const float* wr, const float* wo, const float* bu, const float* br,
+                                     const float* bo, float* gates, float* h, float* rh, int B, int T, int Cx, int Ch,
+                                     int H, int W, int k, void* workspace, size_t ws_bytes, void* stream) {
+  DVD_CHECK_ARG(x && wu && wr && wo && bu && br && bo && gates && h && rh && workspace);
+  DVD_CHECK_ARG(B > 0 && T > 0 && Cx > 0 && Ch > 0 && H > 0 && W > 0 && (k & 1));
+  const int HW = H * W, taps = k * k, Ct = Cx + Ch;
+  GruWs ws = carve(workspace, B, Cx, Ch, HW, taps, false);
+  DVD_CHECK_ARG(ws.bytes <= ws_bytes);
+  cudaStream_t st = as_stream(stream);
+  const float* wsrc[3] = {wu, wr, wo};
+  const float* bsrc[3] = {bu, br, bo};
+  for (int g = 0; g < 3; ++g) {
+    DVD_TRY(dvd_weight_pack(wsrc[g], Ct, taps, 0, Ch, 0, Cx, nullptr, 0, ws.wx, Cx, 0, 3 * Ch, g * Ch, stream));
+    if (g < 2) DVD_TRY(dvd_weight_pack(wsrc[g], Ct, taps, 0, Ch, Cx, Ch, nullptr, 0, ws.whur, Ch, 0, 2 * Ch, g * Ch, stream));
+    else DVD_TRY(dvd_weight_pack(wsrc[g], Ct, taps, 0, Ch, Cx, Ch, nullptr, 0, ws.who, Ch, 0, Ch, 0, stream));
+    DVD_CUDA(cudaMemcpyAsync(ws.bias + g * Ch, bsrc[g], sizeof(float) * Ch, cudaMemcpyDeviceToDevice, st));
+  }
+  const int64_t chw = (int64_t)Ch * HW;
+  const int64_t g_ts = 3 * chw, g_bs = (int64_t)T * g_ts, h_ts = chw, h_bs = (int64_t)T * chw;
+  // x-halves of all gates, all frames: one implicit GEMM
+  {
+    dvd_conv_desc d = base_desc(B, T, Cx, 3 * Ch, H, W, k);
+    d.x_s1 = x_bs; d.x_s2 = x_ts; d.y_s1 = g_bs; d.y_s2 = g_ts;
+    DVD_TRY(dvd_conv_fwd(&d, x, ws.wx, ws.bias, nullptr, gates, stream));
+  }
+  const int eb = ew_blocks((int64_t)B * chw);
+  for (int t = 0; t < T; ++t) {
+    const float* hp = t > 0 ? h + (int64_t)(t - 1) * h_ts : h0;
+    const int64_t hp_bs = t > 0 ? h_bs : chw;
+    float* g_t = gates + (int64_t)t * g_ts;
+    float* rh_t = rh + (int64_t)t * h_ts;
+    if (hp) {
+      dvd_conv_desc d = base_desc(B, 1, Ch, 2 * Ch, H, W, k);
+      d.x_s1 = hp_bs; d.y_s1 = g_bs; d.accumulate = 1;
+      DVD_TRY(dvd_conv_fwd(&d, hp, ws.whur, nullptr, nullptr, g_t, stream));
+    }
+    gru_gate_ur_kernel<<<eb, 256, 0, st>>>(g_t, g_bs, hp, hp_bs, rh_t, h_bs, B, chw);
+    DVD_LAUNCH_CHECK();
+    if (hp) {
+      dvd_conv_desc d = base_desc(B, 1, Ch, Ch, H, W, k);
+      d.x_s1 = h_bs; d.y_s1 = g_bs; d.accumulate = 1;
+      DVD_TRY(dvd_conv_fwd(&d, rh_t, ws.who, nullptr, nullptr, g_t + 2 * chw, stream));
+    }
+    gru_out_kernel<<<eb, 256, 0, st>>>(g_t, g_bs, hp, hp_bs, h + (int64_t)t * h_ts, h_bs, B, chw);
+    DVD_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+extern "C" int dvd_convgru_layer_bwd(const float* x, int64_t x_bs, int64_t x_ts, const float* h0, const float* wu,
+                                     const float* wr, const float* wo, float* gates, const float* h, const float* rh,
+                                     const float* dh, float* dx, float* dh0, float* dwu, float* dwr, float* dwo,
+                                     float* dbu, float* dbr, float* dbo, int B, int T, int Cx, int Ch, int H, int W,
+                                     int k, void* workspace, size_t ws_bytes, void* stream) {
+  DVD_CHECK_ARG(x && wu && wr && wo && gates && h && rh && dh && dx && dwu && dwr && dwo && dbu && dbr && dbo);
+  DVD_CHECK_ARG(workspace && B > 0 && T > 0 && Cx > 0 && Ch > 0 && H > 0 && W > 0 && (k & 1));
+  DVD_CHECK_ARG(dh0 == nullptr || h0 != nullptr);
+  const int HW = H * W, taps = k * k, Ct = Cx + Ch;
+  GruWs ws = carve(workspace, B, Cx, Ch, HW, taps, true);
+  DVD_CHECK_ARG(ws.bytes <= ws_bytes);
+  cudaStream_t st = as_stream(stream);
+  const float* wsrc[3] = {wu, wr, wo};
+  float* dwdst[3] = {dwu, dwr, dwo};
+  float* dbdst[3] = {dbu, dbr, dbo};
+  // dgrad operands (transposed + flipped): [tap'][gate rows (u|r|o)][ci]
+  for (int g = 0; g < 3; ++g) {
+    DVD_TRY(dvd_weight_pack(wsrc[g], Ct, taps, 0, Ch, 0, Cx, nullptr, 1, ws.wxT, 3 * Ch, g * Ch, Cx, 0, stream));
+    if (g < 2) DVD_TRY(dvd_weight_pack(wsrc[g], Ct, taps, 0, Ch, Cx, Ch, nullptr, 1, ws.whurT, 2 * Ch, g * Ch, Ch, 0, stream));
+    else DVD_TRY(dvd_weight_pack(wsrc[g], Ct, taps, 0, Ch, Cx, Ch, nullptr, 1, ws.whoT, Ch, 0, Ch, 0, stream));
+  }
+  const int64_t chw = (int64_t)Ch * HW;
+  const int64_t g_ts = 3 * chw, g_bs = (int64_t)T * g_ts, h_ts = chw, h_bs = (int64_t)T * chw;
+  const int eb = ew_blocks((int64_t)B * chw);
+  float* carry_in = nullptr;
+  float* carry_out = ws.carry0;
+  for (int t = T - 1; t >= 0; --t) {
+    const float* hp = t > 0 ? h + (int64_t)(t - 1) * h_ts : h0;
+    const int64_t hp_bs = t > 0 ? h_bs : chw;
+    float* g_t = gates + (int64_t)t * g_ts;
+    gru_bwd1_kernel<<<eb, 256, 0, st>>>(g_t, g_bs, hp, hp_bs, dh + (int64_t)t * h_ts, h_bs, carry_in, carry_out, B, chw);
+    DVD_LAUNCH_CHECK();
+    if (hp) {
+      dvd_conv_desc d = base_desc(B, 1, Ch, Ch, H, W, k);     // d(rh) = conv_o^T(da_o), h-half
+      d.x_s1 = g_bs; d.y_s1 = chw;
+      DVD_TRY(dvd_conv_fwd(&d, g_t + 2 * chw, ws.whoT, nullptr, nullptr, ws.d_rh, stream));
+    }
+    gru_bwd2_kernel<<<eb, 256, 0, st>>>(g_t, g_bs, hp, hp_bs, ws.d_rh, carry_out, B, chw);
+    DVD_LAUNCH_CHECK();
+    if (hp) {
+      dvd_conv_desc d = base_desc(B, 1, 2 * Ch, Ch, H, W, k);  // dh_prev += conv_u^T(da_u) + conv_r^T(da_r)
+      d.x_s1 = g_bs; d.y_s1 = chw; d.accumulate = 1;
+      DVD_TRY(dvd_conv_fwd(&d, g_t, ws.whurT, nullptr, nullptr, carry_out, stream));
+    }
+    carry_in = carry_out;
+    carry_out = (carry_out == ws.carry0) ? ws.carry1 : ws.carry0;
+  }
+  if (dh0) DVD_CUDA(cudaMemcpyAsync(dh0, carry_in, sizeof(float) * (size_t)B * chw, cudaMemcpyDeviceToDevice, st));
+  // dx for all frames: one implicit GEMM over the (da_u | da_r | da_o) buffer
+  {
+    dvd_conv_desc d = base_desc(B, T, 3 * Ch, Cx, H, W, k);
+    d.x_s1 = g_bs; d.x_s2 = g_ts; d.y_s1 = (int64_t)T * Cx * HW; d.y_s2 = (int64_t)Cx * HW;
+    DVD_TRY(dvd_conv_fwd(&d, gates, ws.wxT, nullptr, nullptr, dx, stream));
+  }
+  // weight gradients, batched over time
+  {
+    dvd_conv_desc d = base_desc(B, T, Cx, 3 * Ch, H, W, k);
+    d.x_s1 = x_bs; d.x_s2 = x_ts; d.y_s1 = g_bs; d.y_s2 = g_ts;
+    DVD_TRY(dvd_conv_wgrad(&d, x, gates, ws.dwx, stream));
+  }
+  {
+    bool have = false;
+    if (T > 1) {
+      dvd_conv_desc d = base_desc(B, T - 1, Ch, 2 * Ch, H, W, k);   // pairs (h_{t-1}, da_t), t = 1..T-1
+      d.x_s1 = h_bs; d.x_s2 = h_ts; d.y_s1 = g_bs; d.y_s2 = g_ts;
+      DVD_TRY(dvd_conv_wgrad(&d, h, gates + g_ts, ws.dwhur, stream));
+      have = true;
+    }
+    if (h0) {
+      dvd_conv_desc d = base_desc(B, 1, Ch, 2 * Ch, H, W, k);
+      d.x_s1 = chw; d.y_s1 = g_bs; d.accumulate = have ? 1 : 0;
+      DVD_TRY(dvd_conv_wgrad(&d, h0, gates, ws.dwhur, stream));
+      have = true;
+    }
+    if (!have) DVD_CUDA(cudaMemsetAsync(ws.dwhur, 0, sizeof(float) * (size_t)taps * Ch * 2 * Ch, st));
+  }
+  {
+    dvd_conv_desc d = base_desc(B, T, Ch, Ch, H, W, k);             // pairs (rh_t, da_o,t)
+    d.x_s1 = h_bs; d.x_s2 = h_ts; d.y_s1 = g_bs; d.y_s2 = g_ts;
+    DVD_TRY(dvd_conv_wgrad(&d, rh, gates + 2 * chw, ws.dwho, stream));
+  }
+  for (int g = 0; g < 3; ++g) {
+    DVD_TRY(dvd_weight_unpack(ws.dwx, 3 * Ch, g * Ch, Ct, taps, 0, Ch, 0, Cx, 0, dwdst[g], stream));
+    if (g < 2) DVD_TRY(dvd_weight_unpack(ws.dwhur, 2 * Ch, g * Ch, Ct, taps, 0, Ch, Cx, Ch, 0, dwdst[g], stream));
+    else DVD_TRY(dvd_weight_unpack(ws.dwho, Ch, 0, Ct, taps, 0, Ch, Cx, Ch, 0, dwdst[g], stream));
+  }
+  DVD_TRY(dvd_channel_sum(gates, B * T, 3 * Ch, HW, g_ts, 0, ws.dbias, ws.dscratch, stream));
+  for (int g = 0; g < 3; ++g)
+    DVD_CUDA(cudaMemcpyAsync(dbdst[g], ws.dbias + g * Ch, sizeof(float) * Ch, cudaMemcpyDeviceToDevice, st));
+  return 0;
+}

@@ -1,0 +1,509 @@
+"""GPU parity tests: the CUDA path (through the C ABI / ctypes binding) against
+  * the golden vectors produced by the unmodified reference (tests/golden/*.pt), and
+  * the CPU oracle (oracle/dvdgan_oracle.py) / plain torch fp32 CPU ops on the same seeded inputs.
+
+Tolerances (north_star: forward within 1e-3 relative fp32, power-iteration count pinned to 1):
+  forward tensors   rel-L2 <= 1e-4 (the fp32 SIMT path only differs by summation order)
+  gradients         rel-L2 <= 1e-3 per tensor (per-kernel, on identical inputs)
+"""
+import copy
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import clone_sd
+
+pytestmark = pytest.mark.gpu
+
+FWD_TOL = 1e-4
+GRAD_TOL = 1e-3
+
+
+def rel(a, b):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from dvdgan_b200 import ops as o
+    return o
+
+
+def check_grads(module, grads, tol=GRAD_TOL):
+    for k, p in module.named_parameters():
+        g = grads.get(k)
+        if g is None:
+            continue
+        assert p.grad is not None, k
+        if g.norm() < 1e-6:                      # analytically zero (conv bias in front of a BatchNorm)
+            assert p.grad.norm().item() < 1e-4, k
+            continue
+        assert rel(p.grad, g) < tol, (k, rel(p.grad, g))
+
+
+def check_state(module, sd_expected, keys=None, tol=1e-5):
+    sd = module.state_dict()
+    for k, v in sd_expected.items():
+        if keys is not None and k not in keys:
+            continue
+        if torch.is_floating_point(v):
+            assert rel(sd[k], v) < tol, (k, rel(sd[k], v))
+        else:
+            assert torch.equal(sd[k].cpu(), v), k
+
+
+# ---------------------------------------------------------------------------------------------------
+# dense engines against plain torch fp32
+# ---------------------------------------------------------------------------------------------------
+CONV_CASES = [
+    # N, Cin, Cout, D, H, W, k
+    (3, 5, 7, 1, 6, 6, (1, 3, 3)),
+    (2, 3, 64, 1, 16, 16, (1, 3, 3)),
+    (2, 64, 3, 1, 8, 8, (1, 3, 3)),
+    (4, 24, 40, 1, 4, 4, (1, 5, 5)),
+    (2, 16, 16, 1, 9, 7, (1, 1, 1)),
+    (2, 6, 10, 4, 6, 6, (3, 3, 3)),
+    (1, 3, 8, 6, 8, 8, (3, 3, 3)),
+    (64, 96, 130, 1, 4, 4, (1, 3, 3)),       # 128x128 tiles + tails
+    (16, 256, 128, 1, 4, 4, (1, 5, 5)),      # small M, deep K: split-K path
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_fwd_dgrad_wgrad(dev, ops, case):
+    N, Ci, Co, D, H, W, k = case
+    torch.manual_seed(hash(case) % 1000)
+    shape = (N, Ci, H, W) if D == 1 else (N, Ci, D, H, W)
+    wshape = (Co, Ci) + (k[1:] if D == 1 else k)
+    x = torch.randn(shape, requires_grad=True)
+    w = (torch.randn(wshape) / (Ci * k[0] * k[1] * k[2]) ** 0.5).requires_grad_(True)
+    b = torch.randn(Co, requires_grad=True)
+    conv = F.conv2d if D == 1 else F.conv3d
+    pad = (k[1] // 2, k[2] // 2) if D == 1 else tuple(kk // 2 for kk in k)
+    y_ref = conv(F.relu(x), w, b, padding=pad)
+    gy = torch.randn_like(y_ref)
+    y_ref.backward(gy)
+    xg = x.detach().to(dev).requires_grad_(True)
+    wg = w.detach().to(dev).requires_grad_(True)
+    bg = b.detach().to(dev).requires_grad_(True)
+    y = ops.conv(xg, wg, bg, in_relu=1)
+    assert rel(y, y_ref) < FWD_TOL
+    y.backward(gy.to(dev))
+    assert rel(xg.grad, x.grad) < FWD_TOL
+    assert rel(wg.grad, w.grad) < FWD_TOL
+    assert rel(bg.grad, b.grad) < FWD_TOL
+
+
+def test_conv_fused_options(dev, ops):
+    """upsample-on-load, residual (upsampled) add, tanh epilogue against the unfused torch graph."""
+    torch.manual_seed(5)
+    x = torch.randn(3, 6, 5, 5, requires_grad=True)
+    w = (torch.randn(4, 6, 3, 3) * 0.2).requires_grad_(True)
+    b = torch.randn(4, requires_grad=True)
+    r = torch.randn(3, 4, 5, 5, requires_grad=True)
+    y_ref = torch.tanh(F.conv2d(F.interpolate(x, scale_factor=2), w, b, padding=1) + F.interpolate(r, scale_factor=2))
+    gy = torch.randn_like(y_ref)
+    y_ref.backward(gy)
+    xg, wg, bg, rg = (t.detach().to(dev).requires_grad_(True) for t in (x, w, b, r))
+    y = ops.conv(xg, wg, bg, res=rg, in_up=1, out_act=2, res_up=1)
+    assert rel(y, y_ref) < FWD_TOL
+    y.backward(gy.to(dev))
+    for a, e in ((xg, x), (wg, w), (bg, b), (rg, r)):
+        assert rel(a.grad, e.grad) < FWD_TOL
+
+
+def test_linear_and_bgemm(dev, ops):
+    torch.manual_seed(6)
+    x = torch.randn(70, 240, requires_grad=True)
+    w = (torch.randn(130, 240) * 0.05).requires_grad_(True)
+    b = torch.randn(130, requires_grad=True)
+    y_ref = F.linear(x, w, b)
+    gy = torch.randn_like(y_ref)
+    y_ref.backward(gy)
+    xg, wg, bg = (t.detach().to(dev).requires_grad_(True) for t in (x, w, b))
+    y = ops.conv(xg, wg, bg)
+    assert rel(y, y_ref) < FWD_TOL
+    y.backward(gy.to(dev))
+    for a, e in ((xg, x), (wg, w), (bg, b)):
+        assert rel(a.grad, e.grad) < FWD_TOL
+    a = torch.randn(37, 65)
+    c = torch.randn(65, 90)
+    assert rel(ops.gemm(a.to(dev), c.to(dev)), a @ c) < FWD_TOL
+    assert rel(ops.gemm(a.t().contiguous().to(dev), c.to(dev), ta=True), a @ c) < FWD_TOL
+    assert rel(ops.gemm(a.to(dev), c.t().contiguous().to(dev), tb=True), a @ c) < FWD_TOL
+
+
+def test_pools_phi_gather(dev, ops, golden):
+    torch.manual_seed(7)
+    for shape, p in (((2, 3, 8, 6), (1, 2, 2)), ((2, 3, 4, 6, 8), (2, 2, 2))):
+        x = torch.randn(shape, requires_grad=True)
+        ref = F.avg_pool2d(x, 2) if len(shape) == 4 else F.avg_pool3d(x, 2)
+        gy = torch.randn_like(ref)
+        ref.backward(gy)
+        xg = x.detach().to(dev).requires_grad_(True)
+        y = ops.AvgPoolFn.apply(xg, *p)
+        y.backward(gy.to(dev))
+        assert rel(y, ref) < 1e-6 and rel(xg.grad, x.grad) < 1e-6
+    x = torch.randn(2, 3, 4, 6, 8, requires_grad=True)
+    for p in ((2, 2, 2), (2, 1, 1)):
+        x.grad = None
+        ref = F.max_pool3d(x, kernel_size=p, stride=p)
+        gy = torch.randn_like(ref)
+        ref.backward(gy)
+        xg = x.detach().to(dev).requires_grad_(True)
+        y = ops.MaxPoolFn.apply(xg, *p)
+        y.backward(gy.to(dev))
+        assert torch.equal(y.cpu(), ref) and torch.equal(xg.grad.cpu(), x.grad)
+    from dvdgan_b200.utils import sample_k_frames, vid_downsample
+    fx = golden("helpers.pt")
+    data = fx["data"].to(dev).requires_grad_(True)
+    torch.manual_seed(fx["seed"])
+    s = sample_k_frames(data, 6, 3)
+    assert torch.equal(s.cpu(), fx["sample_k3"])
+    s.sum().backward()
+    assert float(data.grad.sum()) == pytest.approx(s.numel())
+    torch.manual_seed(fx["seed"])
+    assert torch.equal(sample_k_frames(data, 6, 64).detach().cpu(), fx["data"])
+    phi = vid_downsample(data)
+    assert rel(phi, fx["phi"]) < 1e-6
+    d0 = fx["data"].clone().requires_grad_(True)
+    gy = torch.randn_like(fx["phi"])
+    from oracle import dvdgan_oracle as O
+    O.vid_downsample(d0).backward(gy)
+    data.grad = None
+    phi.backward(gy.to(dev))
+    assert rel(data.grad, d0.grad) < 1e-6
+
+
+# ---------------------------------------------------------------------------------------------------
+# blocks against the golden vectors of the reference
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,cfg", [("cell_k3", (5, 6, 3)), ("cell_k5", (4, 8, 5))])
+def test_convgru_cell(dev, golden, name, cfg):
+    from dvdgan_b200.Module.ConvGRU import ConvGRUCell
+    fx = golden("blocks.pt")[name]
+    cell = ConvGRUCell(*cfg)
+    cell.load_state_dict(fx["sd"])
+    cell.to(dev)
+    x = fx["x"].to(dev).requires_grad_(True)
+    h = fx["h"].to(dev).requires_grad_(True)
+    assert rel(cell(x), fx["y_nostate"]) < FWD_TOL
+    y = cell(x, h)
+    assert rel(y, fx["y"]) < FWD_TOL
+    (y * fx["loss_weight"].to(dev)).sum().backward()
+    check_grads(cell, fx["grads"])
+    assert rel(x.grad, fx["dx"]) < GRAD_TOL and rel(h.grad, fx["dh"]) < GRAD_TOL
+
+
+def test_convgru_sequence(dev, golden):
+    from dvdgan_b200.Module.ConvGRU import ConvGRU
+    fx = golden("blocks.pt")["gru_seq"]
+    gru = ConvGRU(4, hidden_sizes=[4, 8, 4], kernel_sizes=[3, 5, 3], n_layers=3)
+    gru.load_state_dict(fx["sd"])
+    gru.to(dev)
+    # (a) the whole-clip path
+    xs = fx["x"].to(dev).requires_grad_(True)
+    y = gru.forward_sequence(xs)
+    assert rel(y, fx["y"]) < FWD_TOL
+    (y * fx["loss_weight"].to(dev)).sum().backward()
+    check_grads(gru, fx["grads"])
+    assert rel(xs.grad, fx["dx"]) < GRAD_TOL
+    # (b) the reference's per-step API (list of hiddens fed back in)
+    gru.zero_grad()
+    xs2 = fx["x"].to(dev).requires_grad_(True)
+    hid, outs = None, []
+    for t in range(xs2.shape[1]):
+        hid = gru(xs2[:, t], hid)
+        assert isinstance(hid, list) and len(hid) == 3
+        outs.append(hid[-1])
+    y2 = torch.stack(outs, 1)
+    assert rel(y2, fx["y"]) < FWD_TOL
+    (y2 * fx["loss_weight"].to(dev)).sum().backward()
+    check_grads(gru, fx["grads"])
+    assert rel(xs2.grad, fx["dx"]) < GRAD_TOL
+
+
+def test_conditional_norm(dev, golden):
+    from dvdgan_b200.Module.Normalization import ConditionalNorm
+    fx = golden("blocks.pt")["cbn"]
+    cn = ConditionalNorm(5, 7)
+    cn.load_state_dict(fx["sd_pre"])
+    cn.to(dev)
+    x = fx["x"].to(dev).requires_grad_(True)
+    c = fx["cond"].to(dev).requires_grad_(True)
+    y = cn(x, c)
+    assert rel(y, fx["y"]) < FWD_TOL
+    check_state(cn, fx["sd_post"])
+    (y * fx["loss_weight"].to(dev)).sum().backward()
+    check_grads(cn, fx["grads"])
+    assert rel(x.grad, fx["dx"]) < GRAD_TOL and rel(c.grad, fx["dcond"]) < GRAD_TOL
+
+
+@pytest.mark.parametrize("up", [1, 2])
+def test_gresblock(dev, golden, up):
+    from dvdgan_b200.Module.GResBlock import GResBlock
+    fx = golden("blocks.pt")[f"gres_up{up}"]
+    blk = GResBlock(6, 4, n_class=10, upsample_factor=up)
+    blk.load_state_dict(fx["sd_pre"])
+    blk.to(dev)
+    x = fx["x"].to(dev).requires_grad_(True)
+    c = fx["cond"].to(dev).requires_grad_(True)
+    y = blk(x, c)
+    assert rel(y, fx["y"]) < FWD_TOL
+    check_state(blk, fx["sd_post"])
+    (y * fx["loss_weight"].to(dev)).sum().backward()
+    check_grads(blk, fx["grads"])
+    assert rel(x.grad, fx["dx"]) < GRAD_TOL and rel(c.grad, fx["dcond"]) < GRAD_TOL
+    # modular condition rows (what the Generator uses): rows of cond repeat with period 2
+    blk2 = GResBlock(6, 4, n_class=10, upsample_factor=up)
+    blk2.load_state_dict(fx["sd_pre"])
+    blk2.to(dev)
+    y2 = blk2(fx["x"].to(dev), fx["cond"][:2].to(dev))
+    assert rel(y2, fx["y"]) < FWD_TOL
+
+
+@pytest.mark.parametrize("name", ["sn_conv2d", "sn_conv3d", "sn_linear", "sn_embed"])
+def test_spectral_norm(dev, golden, name):
+    import torch.nn as nn
+    from dvdgan_b200.Module.Normalization import SpectralNorm
+    fx = golden("blocks.pt")[name]
+    inner = {"sn_conv2d": lambda: nn.Conv2d(3, 5, 3, padding=1), "sn_conv3d": lambda: nn.Conv3d(2, 4, 3, padding=1),
+             "sn_linear": lambda: nn.Linear(6, 1), "sn_embed": lambda: nn.Embedding(4, 6)}[name]()
+    m = SpectralNorm(inner)
+    assert sorted(m.state_dict().keys()) == sorted(fx["sd_pre"].keys())
+    m.load_state_dict(fx["sd_pre"])
+    m.to(dev)
+    x = fx["x"].to(dev)
+    if x.is_floating_point():
+        x.requires_grad_(True)
+    y = m(x)
+    assert rel(y, fx["y"]) < FWD_TOL
+    check_state(m, fx["sd_mid"], keys=("module.weight_u", "module.weight_v"))
+    (y * fx["loss_weight"].to(dev)).sum().backward()
+    check_grads(m, fx["grads"])
+    if fx["dx"] is not None:
+        assert rel(x.grad, fx["dx"]) < GRAD_TOL
+    with torch.no_grad():
+        y2 = m(fx["x"].to(dev))
+    assert rel(y2, fx["y2"]) < FWD_TOL                       # power iteration state advanced (Q3)
+    check_state(m, fx["sd_post"], keys=("module.weight_u", "module.weight_v"))
+
+
+def test_attention3d(dev, golden):
+    from dvdgan_b200.Module.Attention import SelfAttention
+    fx = golden("blocks.pt")["attn3d"]
+    sa = SelfAttention(8)
+    sa.load_state_dict(fx["sd"])
+    sa.to(dev)
+    x = fx["x"].to(dev).requires_grad_(True)
+    y = sa(x)
+    assert rel(y, fx["y"]) < FWD_TOL
+    (y * fx["loss_weight"].to(dev)).sum().backward()
+    check_grads(sa, fx["grads"])
+    assert rel(x.grad, fx["dx"]) < GRAD_TOL
+    with pytest.raises(AssertionError):
+        sa(torch.randn(1, 8, 3, 4, 4, device=dev))
+
+
+def test_separable_attention(dev, golden):
+    from dvdgan_b200.Module.Attention import SeparableAttn
+    fx = golden("blocks.pt")["sep_attn"]
+    sp = SeparableAttn(4)
+    sp.load_state_dict(fx["sd"])
+    sp.to(dev)
+    x = fx["x"].to(dev).requires_grad_(True)
+    y = sp(x)
+    assert rel(y, fx["y"]) < FWD_TOL
+    (y * fx["loss_weight"].to(dev)).sum().backward()
+    check_grads(sp, fx["grads"])
+    assert rel(x.grad, fx["dx"]) < GRAD_TOL
+
+
+def test_spatial_discriminator(dev, golden):
+    from dvdgan_b200.Module.Discriminators import SpatialDiscriminator
+    fx = golden("spatial_d.pt")
+    Ds = SpatialDiscriminator(chn=2, n_class=3)
+    Ds.load_state_dict(fx["sd_pre"])
+    Ds.to(dev)
+    x = fx["x"].to(dev).requires_grad_(True)
+    out = Ds(x, fx["class_id"].to(dev))
+    assert out.shape == (6,)
+    assert rel(out, fx["out"]) < FWD_TOL
+    check_state(Ds, fx["sd_post"])
+    (out * fx["loss_weight"].to(dev)).sum().backward()
+    check_grads(Ds, fx["grads"])
+    assert rel(x.grad, fx["dx"]) < GRAD_TOL
+    fx2 = golden("spatial_d_second.pt")
+    with torch.no_grad():
+        out2 = Ds(fx["x"].to(dev), fx["class_id"].to(dev))
+    assert rel(out2, fx2["out"]) < FWD_TOL
+    check_state(Ds, fx2["sd_post"])
+
+
+def test_temporal_discriminator(dev, golden):
+    from dvdgan_b200.Module.Discriminators import TemporalDiscriminator
+    fx = golden("temporal_d.pt")
+    Dt = TemporalDiscriminator(chn=2, n_class=3)
+    Dt.load_state_dict(fx["sd_pre"])
+    Dt.to(dev)
+    x = fx["x"].to(dev).requires_grad_(True)
+    out = Dt(x, fx["class_id"].to(dev))
+    assert out.shape == (4,)
+    assert rel(out, fx["out"]) < FWD_TOL
+    check_state(Dt, fx["sd_post"])
+    (out * fx["loss_weight"].to(dev)).sum().backward()
+    check_grads(Dt, fx["grads"])
+    assert rel(x.grad, fx["dx"]) < GRAD_TOL
+
+
+def test_generator(dev, golden):
+    from dvdgan_b200.Module.Generator import Generator
+    fx = golden("generator.pt")
+    cfg = fx["cfg"]
+    G = Generator(in_dim=120, latent_dim=cfg["latent_dim"], n_class=cfg["n_class"], ch=cfg["ch"], n_frames=cfg["T"])
+    G.load_state_dict(fx["sd_pre"])
+    G.to(dev)
+    taps = {}
+    out = G(fx["z"].to(dev), fx["class_id"].to(dev), taps=taps)
+    assert out.shape == fx["out"].shape
+    for k, v in fx["taps"].items():                 # per-stage activations and the pre-tanh tensor
+        assert rel(taps[k], v) < FWD_TOL, (k, rel(taps[k], v))
+    assert rel(out, fx["out"]) < FWD_TOL
+    check_state(G, fx["sd_post_changed"])
+    (out * fx["loss_weight"].to(dev)).sum().backward()
+    check_grads(G, fx["grads"], tol=3e-3)           # end-to-end through 4 ConvGRU stages and 16 CBNs
+    G.eval()
+    with torch.no_grad():
+        out_e = G(fx["z"].to(dev), fx["class_id"].to(dev))
+    assert rel(out_e, fx["eval_out"]) < FWD_TOL
+    check_state(G, fx["eval_sd_post_changed"])
+    # the fused colorize+tanh path equals the tapped one
+    G2 = Generator(in_dim=120, latent_dim=cfg["latent_dim"], n_class=cfg["n_class"], ch=cfg["ch"], n_frames=cfg["T"])
+    G2.load_state_dict(fx["sd_pre"])
+    G2.to(dev)
+    assert rel(G2(fx["z"].to(dev), fx["class_id"].to(dev)), fx["out"]) < FWD_TOL
+
+
+def test_state_dict_roundtrip_and_init(golden):
+    """Constructor parity: same seed -> same initial state as the reference (keys, shapes, values)."""
+    from dvdgan_b200.Module.Generator import Generator
+    fx = golden("generator.pt")
+    torch.manual_seed(1234)
+    G = Generator(in_dim=120, latent_dim=4, n_class=3, ch=2, n_frames=4)
+    sd = G.state_dict()
+    assert list(sd.keys()) == list(fx["sd_pre"].keys())
+    for k in sd:
+        assert sd[k].shape == fx["sd_pre"][k].shape, k
+        if torch.is_floating_point(sd[k]):          # orthogonal_ goes through LAPACK: thread-count dependent
+            assert torch.allclose(sd[k], fx["sd_pre"][k], atol=1e-5), k
+
+
+def test_train_step_golden(dev, golden):
+    """Two full G+Ds+Dt steps (BASELINE.json configs[0] run at 64x64) against the reference's losses/params."""
+    import argparse
+    from dvdgan_b200.trainer import Trainer
+    fx = golden("step.pt")
+    cfg = argparse.Namespace(**fx["cfg"])
+
+    class Loader:
+        def __len__(self):
+            return len(fx["clips"])
+
+        def __iter__(self):
+            return iter(zip(fx["clips"], fx["labels"]))
+    torch.cuda.set_device(dev)
+    tr = Trainer(Loader(), cfg)
+    for net, key in ((tr.G, "G"), (tr.D_s, "Ds"), (tr.D_t, "Dt")):
+        Trainer._load_sd(net, fx["sd_pre"][key])
+    torch.manual_seed(fx["rng_seed"])
+    hist = tr.train()
+    losses = [float(h[k]) for h in hist for k in ("ds_loss", "dt_loss", "g_loss")]
+    assert losses == pytest.approx(fx["losses"], rel=2e-4)
+    # Adam with lr 5e-5: two steps move every weight by <= 1e-4; compare the *updates*
+    for net, key in ((tr.G, "G"), (tr.D_s, "Ds"), (tr.D_t, "Dt")):
+        sd = net.state_dict()
+        num = den = 0.0
+        for k, v in fx["sd_post"][key].items():
+            if not torch.is_floating_point(v):
+                assert torch.equal(sd[k].cpu(), v), (key, k)
+                continue
+            if k.endswith("conv0.module.bias") and key == "G":
+                continue        # analytically-zero gradient (bias before a BatchNorm): Adam's step is +-lr noise
+            ref_delta = v - fx["sd_pre"][key][k]
+            got_delta = sd[k].cpu() - fx["sd_pre"][key][k]
+            num += float((got_delta - ref_delta).norm() ** 2)
+            den += float(ref_delta.norm() ** 2)
+        # beta1 = 0 makes the first Adam step ~ lr * sign(g): an element whose tiny gradient changes sign under
+        # fp32 summation-order noise moves by 2*lr; 0.1 allows 0.25 % such elements
+        assert (num / den) ** 0.5 < 0.1, (key, (num / den) ** 0.5)
+
+
+# ---------------------------------------------------------------------------------------------------
+# against the CPU oracle at BASELINE.json sizes
+# ---------------------------------------------------------------------------------------------------
+def test_generator_full_width_vs_oracle(dev):
+    """ch=32, 48 frames, 64x64, 101 classes (configs[1] shape) at B=1: forward vs the CPU oracle, including
+    the pre-tanh tensor (at default init a large share of outputs saturate at +-1)."""
+    from oracle import dvdgan_oracle as O
+    from dvdgan_b200.Module.Generator import Generator
+    torch.manual_seed(0)
+    T = 48
+    G = Generator(in_dim=120, latent_dim=4, n_class=101, ch=32, n_frames=T)
+    sd = clone_sd(G.state_dict())
+    z = torch.randn(1, 120)
+    cls = torch.randint(0, 101, (1,))
+    taps_ref = {}
+    with torch.no_grad():
+        ref = O.generator_forward(sd, z, cls, T, 32, 4, taps=taps_ref)
+    G.to(dev)
+    taps = {}
+    with torch.no_grad():
+        out = G(z.to(dev), cls.to(dev), taps=taps)
+    assert rel(taps["pre_tanh"], taps_ref["pre_tanh"]) < 1e-3
+    assert rel(out, ref) < 1e-3
+    assert float((out.cpu() - ref).abs().max()) < 5e-3
+
+
+def test_discriminators_full_width_vs_oracle(dev):
+    """chn=32, k=8 / 48 frames at B=64 on the GPU (configs[1]); the oracle checks a 2-clip slice (frames are
+    scored independently, so a slice of the batch is a valid sub-problem)."""
+    from oracle import dvdgan_oracle as O
+    from dvdgan_b200.Module.Discriminators import SpatialDiscriminator, TemporalDiscriminator
+    torch.manual_seed(1)
+    Ds = SpatialDiscriminator(chn=32, n_class=101)
+    Dt = TemporalDiscriminator(chn=32, n_class=101)
+    for net in (Ds, Dt):
+        for n, p in net.named_parameters():
+            if n.endswith("gamma"):
+                p.data.fill_(0.5)
+    sd_s, sd_t = clone_sd(Ds.state_dict()), clone_sd(Dt.state_dict())
+    B = 64
+    xs = torch.rand(B, 8, 3, 64, 64) * 2 - 1
+    xt = torch.rand(B, 3, 48, 32, 32) * 2 - 1
+    cls = torch.randint(0, 101, (B,))
+    with torch.no_grad():
+        ref_s = O.spatial_discriminator(sd_s, xs[:2], cls[:2])
+        ref_t = O.temporal_discriminator(sd_t, xt[:2], cls[:2])
+    Ds.to(dev)
+    Dt.to(dev)
+    with torch.no_grad():
+        out_s = Ds(xs.to(dev), cls.to(dev))
+        out_t = Dt(xt.to(dev), cls.to(dev))
+    assert out_s.shape == (B * 8,) and out_t.shape == (B * 12,)
+    assert rel(out_s[:16], ref_s) < 1e-3
+    assert rel(out_t[:24], ref_t) < 1e-3
+
+
+def test_cpu_tensor_raises():
+    """No CPU fallback: ops refuse host tensors."""
+    from dvdgan_b200 import ops as o
+    with pytest.raises(RuntimeError):
+        o.conv(torch.randn(1, 3, 4, 4), torch.randn(2, 3, 3, 3))
