@@ -27,6 +27,10 @@ class ConvDesc(ctypes.Structure):
 P, I, L, F, Z = c_void_p, c_int, c_int64, c_float, c_size_t
 _SIGS = {
     "dvd_abi_version": (c_int, []),
+    "dvd_launch_count": (ctypes.c_longlong, []),
+    "dvd_prof_enable": (I, [I]),
+    "dvd_prof_read": (I, [I, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
+                          ctypes.POINTER(ctypes.c_longlong)]),
     "dvd_conv_fwd": (I, [ctypes.POINTER(ConvDesc), P, P, P, P, P, P]),
     "dvd_conv_wgrad": (I, [ctypes.POINTER(ConvDesc), P, P, P, P]),
     "dvd_weight_pack": (I, [P, I, I, I, I, I, I, P, I, P, I, I, I, I, P]),

@@ -1,6 +1,7 @@
 // Shared helpers for the dvdgan_b200 CUDA library (sm_100a).
 #pragma once
 #include <cuda_runtime.h>
+#include <atomic>
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
@@ -10,6 +11,11 @@
 namespace dvd {
 
 extern thread_local char g_last_error[512];
+extern std::atomic<long long> g_launches;   // kernels launched by this library (bench.py reports it)
+
+// Optional CUDA-event profiling of the dense engines (category 0: conv fwd/dgrad, 1: wgrad).
+void prof_begin(int category, double flops, cudaStream_t st);
+void prof_end(int category, cudaStream_t st);
 
 inline int fail(const char* fmt, const char* a = "", const char* file = "", int line = 0) {
   snprintf(g_last_error, sizeof(g_last_error), fmt, a, file, line);
@@ -30,6 +36,7 @@ inline int fail(const char* fmt, const char* a = "", const char* file = "", int 
 
 #define DVD_LAUNCH_CHECK()                                                           \
   do {                                                                               \
+    ::dvd::g_launches.fetch_add(1, std::memory_order_relaxed);                       \
     cudaError_t _e = cudaGetLastError();                                             \
     if (_e != cudaSuccess)                                                           \
       return ::dvd::fail("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \

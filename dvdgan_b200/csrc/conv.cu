@@ -307,7 +307,9 @@ static void fill_common(ConvP& p, const dvd_conv_desc* d) {
 template <int BM, int BN, int TM, int TN>
 static int launch_fwd(ConvP& p, cudaStream_t st) {
   dim3 grid(ceil_div(p.M, BM), ceil_div(p.d.Cout, BN), p.nsplit);
+  prof_begin(0, 2.0 * p.M * (double)p.d.Cout * p.d.Cin * p.taps, st);
   conv_fwd_kernel<BM, BN, TM, TN><<<grid, 256, 0, st>>>(p);
+  prof_end(0, st);
   DVD_LAUNCH_CHECK();
   return 0;
 }
@@ -534,8 +536,10 @@ extern "C" int dvd_conv_wgrad(const dvd_conv_desc* d, const float* x, const floa
   if (nsplit > 1 && !d->accumulate)
     DVD_CUDA(cudaMemsetAsync(dwp, 0, sizeof(float) * (size_t)p.taps * d->Cin * d->Cout, st));
   dim3 grid(ceil_div(d->Cin, bc), ceil_div(d->Cout, bo), p.taps * nsplit);
+  prof_begin(1, 2.0 * p.M * (double)d->Cout * d->Cin * p.taps, st);
   if (small) conv_wgrad_kernel<64, 64><<<grid, 256, 0, st>>>(p, dwp, nsplit, pps, atomic_out);
   else conv_wgrad_kernel<128, 128><<<grid, 256, 0, st>>>(p, dwp, nsplit, pps, atomic_out);
+  prof_end(1, st);
   DVD_LAUNCH_CHECK();
   return 0;
 }
@@ -698,6 +702,71 @@ extern "C" int dvd_bgemm(int transA, int transB, int M, int N, int K, float alph
   bgemm_kernel<<<grid, 256, 0, as_stream(stream)>>>(transA, transB, M, N, K, alpha, A, lda, strideA, B, ldb, strideB,
                                                     beta, C, ldc, strideC, bias);
   DVD_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// launch counter + CUDA-event profiler for the dense engines
+// ---------------------------------------------------------------------------------------------
+#include <mutex>
+#include <vector>
+namespace dvd {
+std::atomic<long long> g_launches{0};
+namespace {
+struct ProfRec { cudaEvent_t a, b; double flops; };
+std::mutex g_prof_mu;
+bool g_prof_on = false;
+std::vector<ProfRec> g_prof[2];
+std::vector<ProfRec> g_pool;       // recycled event pairs
+long long g_prof_dropped[2] = {0, 0};
+constexpr size_t kProfMax = 1 << 16;
+}  // namespace
+
+void prof_begin(int cat, double flops, cudaStream_t st) {
+  if (!g_prof_on) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (g_prof[cat].size() >= kProfMax) { ++g_prof_dropped[cat]; return; }
+  ProfRec r;
+  if (!g_pool.empty()) { r = g_pool.back(); g_pool.pop_back(); }
+  else if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
+  r.flops = flops;
+  cudaEventRecord(r.a, st);
+  g_prof[cat].push_back(r);
+}
+void prof_end(int cat, cudaStream_t st) {
+  if (!g_prof_on) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (g_prof[cat].empty() || g_prof_dropped[cat]) return;
+  cudaEventRecord(g_prof[cat].back().b, st);
+}
+}  // namespace dvd
+
+extern "C" long long dvd_launch_count(void) { return dvd::g_launches.load(); }
+
+extern "C" int dvd_prof_enable(int on) {
+  std::lock_guard<std::mutex> lk(dvd::g_prof_mu);
+  dvd::g_prof_on = on != 0;
+  return 0;
+}
+
+extern "C" int dvd_prof_read(int category, double* ms, double* flops, long long* launches) {
+  DVD_CHECK_ARG(category == 0 || category == 1);
+  DVD_CHECK_ARG(ms && flops && launches);
+  std::lock_guard<std::mutex> lk(dvd::g_prof_mu);
+  double t = 0.0, f = 0.0;
+  for (auto& r : dvd::g_prof[category]) {
+    DVD_CUDA(cudaEventSynchronize(r.b));
+    float e = 0.f;
+    DVD_CUDA(cudaEventElapsedTime(&e, r.a, r.b));
+    t += e;
+    f += r.flops;
+    dvd::g_pool.push_back(r);
+  }
+  *ms = t;
+  *flops = f;
+  *launches = (long long)dvd::g_prof[category].size() + dvd::g_prof_dropped[category];
+  dvd::g_prof[category].clear();
+  dvd::g_prof_dropped[category] = 0;
   return 0;
 }
 

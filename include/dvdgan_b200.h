@@ -25,6 +25,13 @@ extern "C" {
 
 const char* dvd_last_error(void);
 int dvd_abi_version(void);
+/* Number of CUDA kernels this library has launched in this process (all threads). */
+long long dvd_launch_count(void);
+/* Measurement aid: while enabled, every launch of the dense engines (category 0: dvd_conv_fwd incl. dgrads,
+ * 1: dvd_conv_wgrad) is bracketed by CUDA events on its stream.  dvd_prof_read waits for the recorded events,
+ * returns the summed device time (ms), algorithmic FLOPs and launch count, and resets the category. */
+int dvd_prof_enable(int on);
+int dvd_prof_read(int category, double* ms, double* flops, long long* launches);
 
 /* ------------------------------------------------------------------------------------------
  * Dense engines

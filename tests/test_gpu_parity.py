@@ -37,14 +37,17 @@ def ops():
     return o
 
 
-def check_grads(module, grads, tol=GRAD_TOL):
+def check_grads(module, grads, tol=GRAD_TOL, zero_suffix=None):
+    scale = max(float(g.norm()) for g in grads.values() if g is not None)
     for k, p in module.named_parameters():
         g = grads.get(k)
         if g is None:
             continue
         assert p.grad is not None, k
-        if g.norm() < 1e-6:                      # analytically zero (conv bias in front of a BatchNorm)
-            assert p.grad.norm().item() < 1e-4, k
+        # analytically zero gradients (a conv bias in front of a BatchNorm is cancelled by the mean
+        # subtraction): both sides are rounding noise -> absolute bound
+        if g.norm() < 1e-5 or (zero_suffix and k.endswith(zero_suffix)):
+            assert p.grad.norm().item() < 1e-4 * max(scale, 1.0), k
             continue
         assert rel(p.grad, g) < tol, (k, rel(p.grad, g))
 
@@ -379,7 +382,7 @@ def test_generator(dev, golden):
     assert rel(out, fx["out"]) < FWD_TOL
     check_state(G, fx["sd_post_changed"])
     (out * fx["loss_weight"].to(dev)).sum().backward()
-    check_grads(G, fx["grads"], tol=3e-3)           # end-to-end through 4 ConvGRU stages and 16 CBNs
+    check_grads(G, fx["grads"], tol=3e-3, zero_suffix="conv0.module.bias")   # end-to-end through 4 ConvGRU stages and 16 CBNs
     G.eval()
     with torch.no_grad():
         out_e = G(fx["z"].to(dev), fx["class_id"].to(dev))
