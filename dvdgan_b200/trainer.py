@@ -64,16 +64,33 @@ class FlatAdam:
                 g[off:off + k].zero_()
             else:
                 src = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
-                ops.call("dvd_axpby", ops.ptr(src), 1.0, 0.0, k, g.data_ptr() + 4 * off)
+                self._copy(src, g, off, k)
         return g
 
+    @staticmethod
+    def _copy(src, flat, off, k):
+        ops.call("dvd_axpby", ops.ptr(src), 1.0, 0.0, k, flat.data_ptr() + 4 * off)
+
+    @staticmethod
+    def _adam(p, g, m, v, lr, b1, b2, eps, t, scale):
+        ops.adam_step(p, g, m, v, lr, b1, b2, eps, t, scale)
+
     def step(self, world_size=1):
+        """gather -> (sum all-reduce across ranks) -> fused Adam with the 1/world_size average folded in."""
         g = self.gather_grads()
         if world_size > 1:
             dist.all_reduce(g, op=dist.ReduceOp.SUM)
         self.t += 1
-        ops.adam_step(self.flat_p, g, self.m, self.v, self.lr, self.betas[0], self.betas[1], self.eps, self.t,
-                      1.0 / world_size)
+        self._adam(self.flat_p, g, self.m, self.v, self.lr, self.betas[0], self.betas[1], self.eps, self.t,
+                   1.0 / world_size)
+
+
+def shard_batch(global_batch, world_size, rank):
+    """Data-parallel sharding of a step's clips: equal contiguous shards, one per rank."""
+    if global_batch % world_size != 0:
+        raise ValueError(f"global batch {global_batch} is not divisible by world size {world_size}")
+    per = global_batch // world_size
+    return slice(rank * per, (rank + 1) * per)
 
 
 def _lr_at(kind, base, t, decay):
