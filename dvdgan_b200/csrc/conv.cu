@@ -6,20 +6,11 @@
 //   m = output pixel (image, d, h, w)   -- contiguous in NC(D)HW => coalesced gathers and stores
 //   K order = (tap outer, ci inner)     -- the tap's shift / zero-padding predicate is hoisted
 #include "common.cuh"
+#include "conv_params.cuh"
 
 namespace dvd {
 
 thread_local char g_last_error[512] = "";
-
-struct ConvP {
-  dvd_conv_desc d;
-  const float* x;
-  const float* w;
-  const float* bias;
-  const float* res;
-  float* y;
-  int M, DHW, HW, taps, Hs, Ws, ck, iters_total, iters_per_split, nsplit, vecB, vecY, atomic_out;
-};
 
 constexpr int BK = 8;
 
@@ -280,6 +271,21 @@ __global__ void zero_view_kernel(float* y, int N2, int Cout, int DHW, int64_t s1
   }
 }
 
+int zero_output_view(const ConvP& p, cudaStream_t st) {
+  const dvd_conv_desc* d = &p.d;
+  const int64_t img = (int64_t)d->Cout * p.DHW;
+  const bool dense_y = (d->y_cs == p.DHW) && (d->N2 == 1 || d->y_s2 == img) &&
+                       (d->N1 == 1 || d->y_s1 == (int64_t)d->N2 * img);
+  const int64_t total = (int64_t)d->N1 * d->N2 * img;
+  if (dense_y) {
+    DVD_CUDA(cudaMemsetAsync(p.y, 0, sizeof(float) * (size_t)total, st));
+  } else {
+    zero_view_kernel<<<ew_blocks(total, 1), 256, 0, st>>>(p.y, d->N2, d->Cout, p.DHW, d->y_s1, d->y_s2, d->y_cs, total);
+    DVD_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
 static int check_desc(const dvd_conv_desc* d) {
   DVD_CHECK_ARG(d != nullptr);
   DVD_CHECK_ARG(d->N1 > 0 && d->N2 > 0 && d->Cin > 0 && d->Cout > 0);
@@ -329,6 +335,8 @@ extern "C" int dvd_conv_fwd(const dvd_conv_desc* d, const float* x, const float*
   p.vecB = (d->Cout % 4 == 0) && ((reinterpret_cast<uintptr_t>(w_packed) & 15) == 0);
   p.vecY = (p.DHW % 4 == 0) && ((reinterpret_cast<uintptr_t>(y) & 15) == 0) && (d->y_s1 % 4 == 0) &&
            (d->y_s2 % 4 == 0) && (d->y_cs % 4 == 0);
+  if (tma_fwd_eligible(p)) return tma_fwd_launch(p, st);
+  if (tc_fwd_eligible(p)) return tc_fwd_launch(p, st);
   const int nsm = num_sms();
   // tile selection
   int tile;  // 0: 128x128  1: 128x64  2: 64x64  3: 256x16
@@ -343,9 +351,6 @@ extern "C" int dvd_conv_fwd(const dvd_conv_desc* d, const float* x, const float*
   int64_t ctas = ctas_of(tile);
   // split-K for under-filled grids (small-spatial ConvGRU stages)
   p.nsplit = 1;
-  const int64_t img = (int64_t)d->Cout * p.DHW;
-  const bool dense_y = (d->y_cs == p.DHW) && (d->N2 == 1 || d->y_s2 == img) &&
-                       (d->N1 == 1 || d->y_s1 == (int64_t)d->N2 * img);
   if (ctas < nsm && d->out_act == 0 && p.iters_total >= 32) {
     int want = (int)ceil_div<int64_t>(2 * nsm, ctas);
     int maxs = p.iters_total / 16;
@@ -356,15 +361,7 @@ extern "C" int dvd_conv_fwd(const dvd_conv_desc* d, const float* x, const float*
   p.iters_per_split = ceil_div(p.iters_total, p.nsplit);
   p.nsplit = ceil_div(p.iters_total, p.iters_per_split);
   p.atomic_out = p.nsplit > 1;
-  if (p.atomic_out && !d->accumulate) {
-    if (dense_y) {
-      DVD_CUDA(cudaMemsetAsync(y, 0, sizeof(float) * (size_t)d->N1 * d->N2 * d->Cout * p.DHW, st));
-    } else {
-      const int64_t total = (int64_t)d->N1 * d->N2 * d->Cout * p.DHW;
-      zero_view_kernel<<<ew_blocks(total, 1), 256, 0, st>>>(y, d->N2, d->Cout, p.DHW, d->y_s1, d->y_s2, d->y_cs, total);
-      DVD_LAUNCH_CHECK();
-    }
-  }
+  if (p.atomic_out && !d->accumulate) DVD_TRY(zero_output_view(p, st));
   switch (tile) {
     case 0: return launch_fwd<128, 128, 8, 8>(p, st);
     case 1: return launch_fwd<128, 64, 8, 4>(p, st);
@@ -519,6 +516,8 @@ extern "C" int dvd_conv_wgrad(const dvd_conv_desc* d, const float* x, const floa
   ConvP p;
   fill_common(p, d);
   p.x = x; p.y = const_cast<float*>(dy); p.w = nullptr; p.bias = nullptr; p.res = nullptr;
+  if (tma_wgrad_eligible(p)) return tma_wgrad_launch(p, dwp, st);
+  if (tc_wgrad_eligible(p)) return tc_wgrad_launch(p, dwp, st);
   const int nsm = num_sms();
   const bool small = (d->Cin <= 64 && d->Cout <= 64);
   const int bc = small ? 64 : 128, bo = small ? 64 : 128;

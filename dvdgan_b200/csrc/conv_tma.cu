@@ -1,0 +1,804 @@
+// TMA + tcgen05 implicit-GEMM convolution (forward / dgrad and weight gradient) for sm_100a.
+//
+// Operand preparation (HBM-bound, once per conv call): the fp32 NC(D)HW activation (or dY) is split into
+// bf16 hi/lo planes in channels-last layout [N][D][H][W][Cp] (ReLU / nearest-x2 upsample of the reference's
+// F.relu / F.interpolate fused in); the fp32 packed weights [tap][Cin][Cout] become [tap][CoutP][CinP] planes.
+// x = hi + lo to ~2^-17, and the GEMM issues  D_main += A_hi*B_hi ,  D_lo += A_lo*B_hi + A_hi*B_lo  into separate
+// fp32 TMEM accumulators (the tensor core's accumulator truncates on every add, so the many small cross terms
+// are kept out of the large accumulator; the two are summed in fp32 in the epilogue).
+//
+// forward CTA (192 threads): warp 0 = TMA producer (one lane), warp 1 = TMEM alloc + tcgen05.mma issuer (one lane),
+// warps 2-5 = epilogue.  A tile = 128 output pixels x 64 channels, fetched per tap as ONE 5-D TMA box
+// (c, w, h, d, n) whose start coordinate carries the tap's shift; out-of-bounds = zero fill = the conv padding.
+// B tile = BN couts x 64 channels, a 2-D box of the prepared weights.  K-major, 128B-swizzled, 2-4 stage ring.
+//
+// wgrad CTA: D[ci][co] += sum_pixels X[pix + tap][ci] * dY[pix][co]: both operands are MN-major views of the same
+// channels-last planes (k = 64 consecutive pixels = one TMA box), one tap and one pixel range per CTA.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include <mutex>
+
+#include "common.cuh"
+#include "conv_params.cuh"
+
+namespace dvd {
+namespace tma {
+
+constexpr int BM = 128;
+constexpr int BKC = 64;
+constexpr int NT = 192;
+
+// ------------------------------------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+// shared-memory matrix descriptor, SWIZZLE_128B.  K-major: rows at 128 B, SBO = 1024 (8-row group).
+// MN-major: 64 MN elements per 128-B row, 8 k-rows per 1024-B atom (SBO), next 64-wide MN block LBO bytes away.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;      // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;      // SWIZZLE_128B
+  return d;
+}
+// kind::f16 instruction descriptor: D = f32, A = B = bf16, M = 128, N = n; mn_major: both operands MN-major
+__device__ __forceinline__ uint32_t make_idesc(int n, int mn_major) {
+  uint32_t d = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+  if (mn_major) d |= (1u << 15) | (1u << 16);
+  return d;
+}
+__device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------------------ operand prep
+// src: fp32, element (n, c, pix) at n1*s1 + n2*s2 + c*cs + srcpix(pix)   ->  dst planes [n][pix][Cp] bf16 hi / lo.
+// Block = 32 output pixels x 64 channels, transposed through shared memory (coalesced on both sides).
+struct PrepP {
+  const float* src;
+  __nv_bfloat16* hi;
+  __nv_bfloat16* lo;
+  int N2, C, Cp;
+  int64_t s1, s2, cs;
+  int in_pix;        // valid output pixels per image (rows >= in_pix are zero-filled)
+  int out_pix;       // rows per image in dst
+  int W, HW, up;     // output W, H*W (for the upsample source map); up = 1: source is (H/2, W/2)
+  int relu;
+};
+
+__global__ void __launch_bounds__(256) prep_planes_kernel(const PrepP p) {
+  __shared__ float tile[64][33];
+  const int n = blockIdx.z;
+  const int pix0 = blockIdx.x * 32;
+  const int c0 = blockIdx.y * 64;
+  const int n1 = n / p.N2, n2 = n - n1 * p.N2;
+  const float* src = p.src + (int64_t)n1 * p.s1 + (int64_t)n2 * p.s2;
+  const int tid = threadIdx.x;
+  {
+    const int px = tid & 31;
+    const int pix = pix0 + px;
+    int64_t so = -1;
+    if (pix < p.in_pix) {
+      if (p.up) {
+        const int z = pix / p.HW;
+        const int r = pix - z * p.HW;
+        const int y = r / p.W, x = r - y * p.W;
+        so = ((int64_t)z * (p.HW >> 2)) + (int64_t)(y >> 1) * (p.W >> 1) + (x >> 1);
+      } else {
+        so = pix;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = (tid >> 5) + 8 * j;
+      float v = 0.f;
+      if (so >= 0 && c0 + c < p.C) {
+        v = __ldg(src + (int64_t)(c0 + c) * p.cs + so);
+        if (p.relu) v = fmaxf(v, 0.f);
+      }
+      tile[c][px] = v;
+    }
+  }
+  __syncthreads();
+  {
+    const int px = tid >> 3, q = tid & 7;
+    const int pix = pix0 + px;
+    if (pix < p.out_pix) {
+      uint32_t h[4], l[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float a = tile[q * 8 + 2 * i][px], b = tile[q * 8 + 2 * i + 1][px];
+        const __nv_bfloat162 hp = __floats2bfloat162_rn(a, b);
+        const float2 hf = __bfloat1622float2(hp);
+        const __nv_bfloat162 lp = __floats2bfloat162_rn(a - hf.x, b - hf.y);
+        h[i] = *reinterpret_cast<const uint32_t*>(&hp);
+        l[i] = *reinterpret_cast<const uint32_t*>(&lp);
+      }
+      const int64_t o = ((int64_t)n * p.out_pix + pix) * p.Cp + c0 + q * 8;
+      *reinterpret_cast<uint4*>(p.hi + o) = make_uint4(h[0], h[1], h[2], h[3]);
+      *reinterpret_cast<uint4*>(p.lo + o) = make_uint4(l[0], l[1], l[2], l[3]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ forward kernel
+struct TileGeom {
+  int bw, bh, bd, bn;      // box extents (w, h, d, images); bw*bh*bd*bn = rows per box
+};
+
+template <int BN>
+struct Cfg {
+  static constexpr int A_BYTES = BM * 128;
+  static constexpr int B_BYTES = BN * 128;
+  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 2 : (BN == 128 ? 3 : 4);
+  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 256;
+  static constexpr int TMEM_COLS = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);   // main | lo
+};
+
+struct FwdP {
+  ConvP c;
+  TileGeom g;
+  int CoutP;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(NT, 1)
+conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                    const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+                    const FwdP fp) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + C::STAGES;
+  uint64_t* accum_bar = bars + 2 * C::STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 1);
+
+  const ConvP& p = fp.c;
+  const dvd_conv_desc& d = p.d;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(smem_u32(full_bar + s), 1);
+      mbar_init(smem_u32(empty_bar + s), 1);
+    }
+    mbar_init(smem_u32(accum_bar), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)C::TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int m0 = blockIdx.x * BM;
+  const int n0 = blockIdx.y * BN;
+  const int it_begin = blockIdx.z * p.iters_per_split;
+  const int it_end = min(it_begin + p.iters_per_split, p.iters_total);
+  const int n_iters = it_end - it_begin;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // box origin of this tile: m0 -> (image, z, y, x); the box covers (bn, bd, bh, bw) = 128 rows
+      const int img = m0 / p.DHW;
+      int rem = m0 - img * p.DHW;
+      const int z0 = rem / p.HW;
+      rem -= z0 * p.HW;
+      const int y0 = rem / d.W;
+      const int x0 = rem - y0 * d.W;
+      int tap = it_begin / p.ck;
+      int cchunk = it_begin - tap * p.ck;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = 0; it < n_iters; ++it) {
+        const int kw = tap % d.kW;
+        const int t2 = tap / d.kW;
+        const int kh = t2 % d.kH;
+        const int kd = t2 / d.kH;
+        mbar_wait(smem_u32(empty_bar + stage), phase ^ 1);
+        const uint32_t fb = smem_u32(full_bar + stage);
+        const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
+        mbar_expect_tx(fb, C::STAGE_BYTES);
+        const int c0 = cchunk * BKC;
+        const int cx = x0 + kw - d.kW / 2, cy = y0 + kh - d.kH / 2, cz = z0 + kd - d.kD / 2;
+        tma_load_5d(sa, &tmA_hi, fb, c0, cx, cy, cz, img);
+        tma_load_5d(sa + C::A_BYTES, &tmA_lo, fb, c0, cx, cy, cz, img);
+        tma_load_2d(sa + 2 * C::A_BYTES, &tmB_hi, fb, c0, tap * fp.CoutP + n0);
+        tma_load_2d(sa + 2 * C::A_BYTES + C::B_BYTES, &tmB_lo, fb, c0, tap * fp.CoutP + n0);
+        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        if (++cchunk == p.ck) { cchunk = 0; ++tap; }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(BN, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = 0; it < n_iters; ++it) {
+        mbar_wait(smem_u32(full_bar + stage), phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
+        const uint64_t a_hi = make_desc(sa, 16, 1024), a_lo = make_desc(sa + C::A_BYTES, 16, 1024);
+        const uint64_t b_hi = make_desc(sa + 2 * C::A_BYTES, 16, 1024);
+        const uint64_t b_lo = make_desc(sa + 2 * C::A_BYTES + C::B_BYTES, 16, 1024);
+#pragma unroll
+        for (int kk = 0; kk < BKC / 16; ++kk) {
+          const uint64_t adv = (uint64_t)(kk * 2);       // 32 bytes along K inside the 128-byte swizzle row
+          const uint32_t acc = (it | kk) != 0;
+          mma_f16(tmem_base, a_hi + adv, b_hi + adv, idesc, acc);
+          mma_f16(tmem_base + BN, a_lo + adv, b_hi + adv, idesc, acc);
+          mma_f16(tmem_base + BN, a_hi + adv, b_lo + adv, idesc, 1);
+        }
+        mma_commit(smem_u32(empty_bar + stage));
+        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+      }
+      mma_commit(smem_u32(accum_bar));
+    }
+    __syncwarp();
+  } else {
+    // ---------------- epilogue: warps 2..5; a warp may only touch TMEM lanes [32*(warp%4), +32)
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int m = m0 + row;
+    const bool ok = m < p.M;
+    int64_t yo = 0, ro = 0;
+    if (ok) {
+      const int n = m / p.DHW;
+      const int rem = m - n * p.DHW;
+      const int n1 = n / d.N2, n2 = n - n1 * d.N2;
+      yo = (int64_t)n1 * d.y_s1 + (int64_t)n2 * d.y_s2 + rem;
+      if (p.res) {
+        int rr = rem;
+        if (d.res_up) {
+          const int z = rem / p.HW;
+          const int r2 = rem - z * p.HW;
+          const int hh = r2 / d.W, ww = r2 - hh * d.W;
+          rr = (z * (d.H >> 1) + (hh >> 1)) * (d.W >> 1) + (ww >> 1);
+        }
+        ro = (int64_t)n1 * d.r_s1 + (int64_t)n2 * d.r_s2 + rr;
+      }
+    }
+    const bool lead = blockIdx.z == 0;
+    mbar_wait(smem_u32(accum_bar), 0);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+    for (int cb = 0; cb < BN; cb += 32) {
+      if (n0 + cb >= d.Cout) break;
+      uint32_t r0[32], r1[32];
+      tmem_ld32(taddr + cb, r0);
+      tmem_ld32(taddr + BN + cb, r1);
+      tmem_ld_wait();
+      if (!ok) continue;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int co = n0 + cb + j;
+        if (co >= d.Cout) break;
+        float v = __uint_as_float(r0[j]) + __uint_as_float(r1[j]);
+        if (lead) {
+          if (p.bias) v += __ldg(p.bias + co);
+          if (p.res) v += __ldg(p.res + ro + (int64_t)co * d.r_cs);
+        }
+        float* dst = p.y + yo + (int64_t)co * d.y_cs;
+        if (p.atomic_out) {
+          atomicAdd(dst, v);
+        } else {
+          if (d.accumulate) v += *dst;
+          if (d.out_act == 1) v = fmaxf(v, 0.f);
+          else if (d.out_act == 2) v = tanhf(v);
+          *dst = v;
+        }
+      }
+    }
+    tc_fence_before();
+  }
+
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ wgrad kernel
+// A = X^T (rows ci, MN-major), B = dY^T (rows co, MN-major), k = 64 pixels per stage.
+struct WgP {
+  ConvP c;
+  TileGeom g;           // box of 64 pixels
+  int nsplit, per_split;   // pixel range per CTA (multiple of 64)
+};
+
+template <int BN>
+struct WCfg {
+  static constexpr int A_BYTES = 2 * 64 * 128;           // 128 ci = two 64-wide MN blocks of [64 k][128 B]
+  static constexpr int B_BYTES = (BN / 64) * 64 * 128;
+  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 2 : (BN == 128 ? 3 : 4);
+  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 256;
+  static constexpr int TMEM_COLS = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
+};
+
+template <int BN>
+__global__ void __launch_bounds__(NT, 1)
+conv_tma_wgrad_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant__ CUtensorMap tmX_lo,
+                      const __grid_constant__ CUtensorMap tmY_hi, const __grid_constant__ CUtensorMap tmY_lo,
+                      const WgP wp, float* __restrict__ dwp) {
+  using C = WCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + C::STAGES;
+  uint64_t* accum_bar = bars + 2 * C::STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 1);
+
+  const ConvP& p = wp.c;
+  const dvd_conv_desc& d = p.d;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(smem_u32(full_bar + s), 1);
+      mbar_init(smem_u32(empty_bar + s), 1);
+    }
+    mbar_init(smem_u32(accum_bar), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)C::TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int ci0 = blockIdx.x * BM;
+  const int co0 = blockIdx.y * BN;
+  const int tap = blockIdx.z / wp.nsplit;
+  const int split = blockIdx.z - tap * wp.nsplit;
+  const int m_lo = split * wp.per_split;
+  const int m_hi = min(m_lo + wp.per_split, p.M);
+  const int n_iters = (m_hi - m_lo + BKC - 1) / BKC;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const int kw = tap % d.kW;
+      const int t2 = tap / d.kW;
+      const int kh = t2 % d.kH;
+      const int kd = t2 / d.kH;
+      const int ox = kw - d.kW / 2, oy = kh - d.kH / 2, oz = kd - d.kD / 2;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = 0; it < n_iters; ++it) {
+        const int mk = m_lo + it * BKC;
+        const int img = mk / p.DHW;
+        int rem = mk - img * p.DHW;
+        const int z0 = rem / p.HW;
+        rem -= z0 * p.HW;
+        const int y0 = rem / d.W;
+        const int x0 = rem - y0 * d.W;
+        mbar_wait(smem_u32(empty_bar + stage), phase ^ 1);
+        const uint32_t fb = smem_u32(full_bar + stage);
+        const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
+        mbar_expect_tx(fb, C::STAGE_BYTES);
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+          tma_load_5d(sa + b * 8192, &tmX_hi, fb, ci0 + b * 64, x0 + ox, y0 + oy, z0 + oz, img);
+          tma_load_5d(sa + C::A_BYTES + b * 8192, &tmX_lo, fb, ci0 + b * 64, x0 + ox, y0 + oy, z0 + oz, img);
+        }
+#pragma unroll
+        for (int b = 0; b < BN / 64; ++b) {
+          tma_load_5d(sa + 2 * C::A_BYTES + b * 8192, &tmY_hi, fb, co0 + b * 64, x0, y0, z0, img);
+          tma_load_5d(sa + 2 * C::A_BYTES + C::B_BYTES + b * 8192, &tmY_lo, fb, co0 + b * 64, x0, y0, z0, img);
+        }
+        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(BN, 1);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = 0; it < n_iters; ++it) {
+        mbar_wait(smem_u32(full_bar + stage), phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
+        // MN-major: LBO = 8192 (next 64-wide MN block), SBO = 1024 (next 8 k-rows)
+        const uint64_t a_hi = make_desc(sa, 8192, 1024), a_lo = make_desc(sa + C::A_BYTES, 8192, 1024);
+        const uint64_t b_hi = make_desc(sa + 2 * C::A_BYTES, 8192, 1024);
+        const uint64_t b_lo = make_desc(sa + 2 * C::A_BYTES + C::B_BYTES, 8192, 1024);
+#pragma unroll
+        for (int kk = 0; kk < BKC / 16; ++kk) {
+          const uint64_t adv = (uint64_t)(kk * 2048 >> 4);     // 16 k-rows of 128 bytes
+          const uint32_t acc = (it | kk) != 0;
+          mma_f16(tmem_base, a_hi + adv, b_hi + adv, idesc, acc);
+          mma_f16(tmem_base + BN, a_lo + adv, b_hi + adv, idesc, acc);
+          mma_f16(tmem_base + BN, a_hi + adv, b_lo + adv, idesc, 1);
+        }
+        mma_commit(smem_u32(empty_bar + stage));
+        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+      }
+      mma_commit(smem_u32(accum_bar));
+    }
+    __syncwarp();
+  } else {
+    const int q = warp & 3;
+    const int ci = ci0 + q * 32 + lane;
+    const bool ok = ci < d.Cin;
+    mbar_wait(smem_u32(accum_bar), 0);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+    for (int cb = 0; cb < BN; cb += 32) {
+      if (co0 + cb >= d.Cout) break;
+      uint32_t r0[32], r1[32];
+      tmem_ld32(taddr + cb, r0);
+      tmem_ld32(taddr + BN + cb, r1);
+      tmem_ld_wait();
+      if (!ok) continue;
+      float* dst = dwp + ((int64_t)tap * d.Cin + ci) * d.Cout + co0 + cb;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        if (co0 + cb + j >= d.Cout) break;
+        const float v = __uint_as_float(r0[j]) + __uint_as_float(r1[j]);
+        if (p.atomic_out) atomicAdd(dst + j, v);
+        else dst[j] = v;
+      }
+    }
+    tc_fence_before();
+  }
+
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                             const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                             CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeFn get_encode() {
+  static EncodeFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeFn>(ptr);
+  });
+  return fn;
+}
+
+// channels-last planes [N][D][H][W][Cp] -> 5-D map (c, w, h, d, n), box (64, bw, bh, bd, bn), 128B swizzle
+static int make_act_map(CUtensorMap* tm, const void* base, int N, int D, int H, int W, int Cp, const TileGeom& g) {
+  EncodeFn enc = get_encode();
+  if (!enc) return fail("cuTensorMapEncodeTiled unavailable%s (%s:%d)", "", __FILE__, __LINE__);
+  cuuint64_t gdim[5] = {(cuuint64_t)Cp, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
+  cuuint64_t gstr[4] = {(cuuint64_t)Cp * 2, (cuuint64_t)W * Cp * 2, (cuuint64_t)H * W * Cp * 2,
+                        (cuuint64_t)D * H * W * Cp * 2};
+  cuuint32_t box[5] = {64, (cuuint32_t)g.bw, (cuuint32_t)g.bh, (cuuint32_t)g.bd, (cuuint32_t)g.bn};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled (activation) failed%s (%s:%d)", "", __FILE__, __LINE__);
+  return 0;
+}
+
+static int make_w_map(CUtensorMap* tm, const void* base, int rows, int Cp, int box_rows) {
+  EncodeFn enc = get_encode();
+  if (!enc) return fail("cuTensorMapEncodeTiled unavailable%s (%s:%d)", "", __FILE__, __LINE__);
+  cuuint64_t gdim[2] = {(cuuint64_t)Cp, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)Cp * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled (weights) failed%s (%s:%d)", "", __FILE__, __LINE__);
+  return 0;
+}
+
+// rows consecutive flat pixels (rows = 128 or 64) as a box (bn, bd, bh, bw); false if the geometry does not tile
+static bool tile_geom(int rows, int N, int D, int H, int W, TileGeom* g) {
+  if (W > rows || rows % W) return false;
+  g->bw = W;
+  int left = rows / W;
+  g->bh = H < left ? H : left;
+  if (H % g->bh || left % g->bh) return false;
+  left /= g->bh;
+  g->bd = D < left ? D : left;
+  if (D % g->bd || left % g->bd) return false;
+  left /= g->bd;
+  g->bn = left;
+  if (g->bn > 256) return false;
+  // a box must not straddle: if it spans several rows it must span full rows etc. (guaranteed by construction:
+  // bh < H only when bd = bn = 1; bd < D only when bn = 1)
+  if (g->bh < H && (g->bd != 1 || g->bn != 1)) return false;
+  if (g->bd < D && g->bn != 1) return false;
+  (void)N;
+  return true;
+}
+
+static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+struct Scratch {
+  void* ptr = nullptr;
+  cudaStream_t st;
+  int alloc(size_t bytes, cudaStream_t s) {
+    st = s;
+    static std::once_flag once;
+    std::call_once(once, [] {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaMemPool_t pool;
+      if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        uint64_t thr = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+      }
+    });
+    DVD_CUDA(cudaMallocAsync(&ptr, bytes, s));
+    return 0;
+  }
+  ~Scratch() {
+    if (ptr) cudaFreeAsync(ptr, st);
+  }
+};
+
+static int prep_planes(const float* src, int N1, int N2, int C, int Cp, int64_t s1, int64_t s2, int64_t cs, int in_pix,
+                       int out_pix, int W, int HW, int up, int relu, __nv_bfloat16* hi, __nv_bfloat16* lo,
+                       cudaStream_t st) {
+  PrepP p;
+  p.src = src; p.hi = hi; p.lo = lo; p.N2 = N2; p.C = C; p.Cp = Cp; p.s1 = s1; p.s2 = s2; p.cs = cs;
+  p.in_pix = in_pix; p.out_pix = out_pix; p.W = W; p.HW = HW; p.up = up; p.relu = relu;
+  const int N = N1 * N2;
+  DVD_CHECK_ARG(N <= 65535 * 64);
+  // gridDim.z <= 65535: fold large image counts
+  DVD_CHECK_ARG(N <= 65535);
+  dim3 grid(ceil_div(out_pix, 32), Cp / 64, N);
+  prep_planes_kernel<<<grid, 256, 0, st>>>(p);
+  DVD_LAUNCH_CHECK();
+  return 0;
+}
+
+template <int BN>
+static int launch_fwd(const CUtensorMap* m, const FwdP& fp, dim3 grid, cudaStream_t st) {
+  using C = Cfg<BN>;
+  static bool configured = false;
+  if (!configured) {
+    DVD_CUDA(cudaFuncSetAttribute(conv_tma_fwd_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    configured = true;
+  }
+  conv_tma_fwd_kernel<BN><<<grid, NT, C::SMEM, st>>>(m[0], m[1], m[2], m[3], fp);
+  return 0;
+}
+template <int BN>
+static int launch_wgrad(const CUtensorMap* m, const WgP& wp, float* dwp, dim3 grid, cudaStream_t st) {
+  using C = WCfg<BN>;
+  static bool configured = false;
+  if (!configured) {
+    DVD_CUDA(cudaFuncSetAttribute(conv_tma_wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    configured = true;
+  }
+  conv_tma_wgrad_kernel<BN><<<grid, NT, C::SMEM, st>>>(m[0], m[1], m[2], m[3], wp, dwp);
+  return 0;
+}
+
+}  // namespace tma
+
+// env DVD_CONV_IMPL: "simt" = fp32 FFMA only, "tc" = register-staged tcgen05 (v1), default = TMA tcgen05
+static int impl_pref2() {
+  static int pref = -1;
+  if (pref < 0) {
+    const char* e = getenv("DVD_CONV_IMPL");
+    pref = (e && strcmp(e, "simt") == 0) ? 0 : ((e && strcmp(e, "tc") == 0) ? 1 : 2);
+  }
+  return pref;
+}
+
+bool tma_fwd_eligible(const ConvP& p) {
+  if (impl_pref2() != 2) return false;
+  const dvd_conv_desc& d = p.d;
+  if (d.Cin < 32 || d.Cout < 64 || p.M < 128) return false;
+  if ((int64_t)d.N1 * d.N2 > 65535) return false;
+  tma::TileGeom g;
+  return tma::tile_geom(128, d.N1 * d.N2, d.D, d.H, d.W, &g) && tma::get_encode() != nullptr;
+}
+
+int tma_fwd_launch(ConvP& p, cudaStream_t st) {
+  using namespace tma;
+  const dvd_conv_desc& d = p.d;
+  const int nsm = num_sms();
+  const int N = d.N1 * d.N2;
+  FwdP fp;
+  if (!tile_geom(128, N, d.D, d.H, d.W, &fp.g)) return fail("internal: geometry%s (%s:%d)", "", __FILE__, __LINE__);
+  int bn = d.Cout >= 256 ? 256 : (d.Cout >= 128 ? 128 : 64);
+  const int mt = ceil_div(p.M, BM);
+  if (bn == 256 && (int64_t)mt * ceil_div(d.Cout, 256) < nsm) bn = 128;
+  const int CinP = round_up(d.Cin, 64), CoutP = round_up(d.Cout, bn);
+  fp.CoutP = CoutP;
+  p.ck = CinP / 64;
+  p.iters_total = p.taps * p.ck;
+  const int64_t ctas = (int64_t)mt * ceil_div(d.Cout, bn);
+  int nsplit = 1;
+  if (ctas < nsm && d.out_act == 0 && p.iters_total >= 8) {
+    nsplit = (int)ceil_div<int64_t>(nsm, ctas);
+    const int maxs = p.iters_total / 4;
+    if (nsplit > maxs) nsplit = maxs;
+    if (nsplit > 16) nsplit = 16;
+    if (nsplit < 1) nsplit = 1;
+  }
+  const int per = ceil_div(p.iters_total, nsplit);
+  nsplit = ceil_div(p.iters_total, per);
+  p.nsplit = nsplit;
+  p.iters_per_split = per;
+  p.atomic_out = nsplit > 1;
+  if (p.atomic_out && !d.accumulate) DVD_TRY(zero_output_view(p, st));
+
+  // ---- operand preparation in stream-ordered scratch
+  const int64_t pix = (int64_t)p.DHW;
+  const size_t a_elems = (size_t)N * pix * CinP;
+  const size_t w_elems = (size_t)p.taps * CoutP * CinP;
+  Scratch sc;
+  DVD_TRY(sc.alloc((2 * a_elems + 2 * w_elems) * sizeof(__nv_bfloat16) + 1024, st));
+  __nv_bfloat16* a_hi = reinterpret_cast<__nv_bfloat16*>(sc.ptr);
+  __nv_bfloat16* a_lo = a_hi + a_elems;
+  __nv_bfloat16* w_hi = a_lo + a_elems;
+  __nv_bfloat16* w_lo = w_hi + w_elems;
+  DVD_TRY(prep_planes(p.x, d.N1, d.N2, d.Cin, CinP, d.x_s1, d.x_s2, d.x_cs, p.DHW, p.DHW, d.W, p.HW, d.in_up,
+                      d.in_relu, a_hi, a_lo, st));
+  // weights: [tap][Cin][Cout] fp32 -> [tap][CoutP][CinP]   (image = tap, channel = cin, pixel = cout)
+  DVD_TRY(prep_planes(p.w, p.taps, 1, d.Cin, CinP, (int64_t)d.Cin * d.Cout, 0, d.Cout, d.Cout, CoutP, 1, 1, 0, 0,
+                      w_hi, w_lo, st));
+  CUtensorMap maps[4];
+  DVD_TRY(make_act_map(&maps[0], a_hi, N, d.D, d.H, d.W, CinP, fp.g));
+  DVD_TRY(make_act_map(&maps[1], a_lo, N, d.D, d.H, d.W, CinP, fp.g));
+  DVD_TRY(make_w_map(&maps[2], w_hi, p.taps * CoutP, CinP, bn));
+  DVD_TRY(make_w_map(&maps[3], w_lo, p.taps * CoutP, CinP, bn));
+  fp.c = p;
+  dim3 grid(mt, ceil_div(d.Cout, bn), nsplit);
+  prof_begin(0, 2.0 * p.M * (double)d.Cout * d.Cin * p.taps, st);
+  int rc;
+  if (bn == 256) rc = launch_fwd<256>(maps, fp, grid, st);
+  else if (bn == 128) rc = launch_fwd<128>(maps, fp, grid, st);
+  else rc = launch_fwd<64>(maps, fp, grid, st);
+  prof_end(0, st);
+  if (rc) return rc;
+  DVD_LAUNCH_CHECK();
+  return 0;
+}
+
+bool tma_wgrad_eligible(const ConvP& p) {
+  if (impl_pref2() != 2) return false;
+  const dvd_conv_desc& d = p.d;
+  if (d.Cin < 32 || d.Cout < 64 || p.M < 4096 || d.in_up) return false;
+  if ((int64_t)d.N1 * d.N2 > 65535) return false;
+  if (p.DHW % 64 != 0 && 64 % p.DHW != 0) return false;
+  tma::TileGeom g;
+  return tma::tile_geom(64, d.N1 * d.N2, d.D, d.H, d.W, &g) && tma::get_encode() != nullptr;
+}
+
+int tma_wgrad_launch(ConvP& p, float* dwp, cudaStream_t st) {
+  using namespace tma;
+  const dvd_conv_desc& d = p.d;
+  const int nsm = num_sms();
+  const int N = d.N1 * d.N2;
+  WgP wp;
+  if (!tile_geom(64, N, d.D, d.H, d.W, &wp.g)) return fail("internal: geometry%s (%s:%d)", "", __FILE__, __LINE__);
+  const int bn = d.Cout >= 256 ? 256 : (d.Cout >= 128 ? 128 : 64);
+  const int64_t base = (int64_t)ceil_div(d.Cin, BM) * ceil_div(d.Cout, bn) * p.taps;
+  int nsplit = 1;
+  if (base < 2 * nsm) {
+    nsplit = (int)ceil_div<int64_t>(2 * nsm, base);
+    const int maxs = p.M / 2048 > 0 ? p.M / 2048 : 1;
+    if (nsplit > maxs) nsplit = maxs;
+  }
+  int per = ceil_div(p.M, nsplit);
+  per = round_up(per, BKC);
+  nsplit = ceil_div(p.M, per);
+  p.atomic_out = (nsplit > 1) || d.accumulate;
+  if (nsplit > 1 && !d.accumulate)
+    DVD_CUDA(cudaMemsetAsync(dwp, 0, sizeof(float) * (size_t)p.taps * d.Cin * d.Cout, st));
+  wp.nsplit = nsplit;
+  wp.per_split = per;
+
+  const int CinP = round_up(d.Cin, 64), CoutP = round_up(d.Cout, 64);
+  const size_t x_elems = (size_t)N * p.DHW * CinP, y_elems = (size_t)N * p.DHW * CoutP;
+  Scratch sc;
+  DVD_TRY(sc.alloc((2 * x_elems + 2 * y_elems) * sizeof(__nv_bfloat16) + 1024, st));
+  __nv_bfloat16* x_hi = reinterpret_cast<__nv_bfloat16*>(sc.ptr);
+  __nv_bfloat16* x_lo = x_hi + x_elems;
+  __nv_bfloat16* y_hi = x_lo + x_elems;
+  __nv_bfloat16* y_lo = y_hi + y_elems;
+  DVD_TRY(prep_planes(p.x, d.N1, d.N2, d.Cin, CinP, d.x_s1, d.x_s2, d.x_cs, p.DHW, p.DHW, d.W, p.HW, 0, d.in_relu,
+                      x_hi, x_lo, st));
+  DVD_TRY(prep_planes(p.y, d.N1, d.N2, d.Cout, CoutP, d.y_s1, d.y_s2, d.y_cs, p.DHW, p.DHW, d.W, p.HW, 0, 0, y_hi,
+                      y_lo, st));
+  CUtensorMap maps[4];
+  DVD_TRY(make_act_map(&maps[0], x_hi, N, d.D, d.H, d.W, CinP, wp.g));
+  DVD_TRY(make_act_map(&maps[1], x_lo, N, d.D, d.H, d.W, CinP, wp.g));
+  DVD_TRY(make_act_map(&maps[2], y_hi, N, d.D, d.H, d.W, CoutP, wp.g));
+  DVD_TRY(make_act_map(&maps[3], y_lo, N, d.D, d.H, d.W, CoutP, wp.g));
+  wp.c = p;
+  dim3 grid(ceil_div(d.Cin, BM), ceil_div(d.Cout, bn), p.taps * nsplit);
+  prof_begin(1, 2.0 * p.M * (double)d.Cout * d.Cin * p.taps, st);
+  int rc;
+  if (bn == 256) rc = launch_wgrad<256>(maps, wp, dwp, grid, st);
+  else if (bn == 128) rc = launch_wgrad<128>(maps, wp, dwp, grid, st);
+  else rc = launch_wgrad<64>(maps, wp, dwp, grid, st);
+  prof_end(1, st);
+  if (rc) return rc;
+  DVD_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace dvd

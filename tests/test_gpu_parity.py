@@ -77,6 +77,12 @@ CONV_CASES = [
     (1, 3, 8, 6, 8, 8, (3, 3, 3)),
     (64, 96, 130, 1, 4, 4, (1, 3, 3)),       # 128x128 tiles + tails
     (16, 256, 128, 1, 4, 4, (1, 5, 5)),      # small M, deep K: split-K path
+    # shapes that take the tcgen05 BF16x3 path (Cin >= 32, Cout >= 64, >= 128 pixels; wgrad >= 4096 pixels)
+    (16, 128, 256, 1, 16, 16, (1, 3, 3)),
+    (4, 64, 64, 1, 32, 32, (1, 5, 5)),
+    (5, 96, 200, 1, 32, 32, (1, 3, 3)),      # ragged Cin / Cout / pixel tails
+    (2, 64, 128, 4, 32, 32, (3, 3, 3)),
+    (6, 256, 384, 1, 32, 32, (1, 1, 1)),
 ]
 
 
