@@ -21,7 +21,7 @@ class ConvDesc(ctypes.Structure):
                 ("x_s1", c_int64), ("x_s2", c_int64), ("x_cs", c_int64),
                 ("y_s1", c_int64), ("y_s2", c_int64), ("y_cs", c_int64),
                 ("in_relu", c_int), ("in_up", c_int), ("accumulate", c_int), ("out_act", c_int), ("res_up", c_int),
-                ("r_s1", c_int64), ("r_s2", c_int64), ("r_cs", c_int64)]
+                ("r_s1", c_int64), ("r_s2", c_int64), ("r_cs", c_int64), ("x_kind", c_int)]
 
 
 P, I, L, F, Z = c_void_p, c_int, c_int64, c_float, c_size_t

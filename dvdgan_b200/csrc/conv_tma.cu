@@ -3,9 +3,15 @@
 // Operand preparation (HBM-bound, once per conv call): the fp32 NC(D)HW activation (or dY) is split into
 // bf16 hi/lo planes in channels-last layout [N][D][H][W][Cp] (ReLU / nearest-x2 upsample of the reference's
 // F.relu / F.interpolate fused in); the fp32 packed weights [tap][Cin][Cout] become [tap][CoutP][CinP] planes.
-// x = hi + lo to ~2^-17, and the GEMM issues  D_main += A_hi*B_hi ,  D_lo += A_lo*B_hi + A_hi*B_lo  into separate
-// fp32 TMEM accumulators (the tensor core's accumulator truncates on every add, so the many small cross terms
-// are kept out of the large accumulator; the two are summed in fp32 in the epilogue).
+// x = hi + lo/s.  Forward convolutions (activations x weights, bounded magnitudes) use fp16 planes: hi = fp16(x),
+// lo = fp16((x - hi) * 2^11), so hi + lo/2^11 = x to 2^-24.  Anything that touches gradients (dgrad, wgrad) needs
+// bf16's exponent range: hi = bf16(x), lo = bf16((x - hi) * 2^8), x to 2^-17.  (A and B of one tcgen05.mma must
+// share a format: mixed fp16/bf16 descriptors raise an illegal-instruction fault.)  The GEMM issues
+//   D_main += A_hi*B_hi ,   D_lo += A_lo*B_hi + A_hi*B_lo          (result = D_main + D_lo / s)
+// into separate fp32 TMEM accumulators.  The tensor core truncates its accumulator on every add (measured: error
+// grows linearly with K), so (a) the many small cross terms are kept out of the large accumulator and (b) with
+// PROMOTE the main accumulator ping-pongs between two TMEM regions in chunks of 8 k-blocks; the epilogue warps
+// drain each finished chunk into fp32 registers (round-to-nearest adds) while the next chunk is being issued.
 //
 // forward CTA (192 threads): warp 0 = TMA producer (one lane), warp 1 = TMEM alloc + tcgen05.mma issuer (one lane),
 // warps 2-5 = epilogue.  A tile = 128 output pixels x 64 channels, fetched per tap as ONE 5-D TMA box
@@ -16,6 +22,7 @@
 // channels-last planes (k = 64 consecutive pixels = one TMA box), one tap and one pixel range per CTA.
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include <mutex>
 
@@ -77,9 +84,10 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
   d |= (uint64_t)2 << 61;      // SWIZZLE_128B
   return d;
 }
-// kind::f16 instruction descriptor: D = f32, A = B = bf16, M = 128, N = n; mn_major: both operands MN-major
-__device__ __forceinline__ uint32_t make_idesc(int n, int mn_major) {
-  uint32_t d = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+// kind::f16 instruction descriptor: D = f32, A/B = bf16 (fmt 1) or fp16 (fmt 0), M = 128, N = n;
+// mn_major: both operands MN-major
+__device__ __forceinline__ uint32_t make_idesc(int n, int mn_major, uint32_t a_fmt = 1, uint32_t b_fmt = 1) {
+  uint32_t d = (1u << 4) | (a_fmt << 7) | (b_fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
   if (mn_major) d |= (1u << 15) | (1u << 16);
   return d;
 }
@@ -120,7 +128,10 @@ struct PrepP {
   int out_pix;       // rows per image in dst
   int W, HW, up;     // output W, H*W (for the upsample source map); up = 1: source is (H/2, W/2)
   int relu;
+  int fp16;          // 1: fp16 planes, lo = (x - hi) * 2^11 (forward operands); 0: bf16 planes, lo = (x - hi) * 2^8
 };
+
+constexpr float kLoScaleBf16 = 256.f, kLoScaleFp16 = 2048.f;
 
 __global__ void __launch_bounds__(256) prep_planes_kernel(const PrepP p) {
   __shared__ float tile[64][33];
@@ -164,11 +175,21 @@ __global__ void __launch_bounds__(256) prep_planes_kernel(const PrepP p) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const float a = tile[q * 8 + 2 * i][px], b = tile[q * 8 + 2 * i + 1][px];
-        const __nv_bfloat162 hp = __floats2bfloat162_rn(a, b);
-        const float2 hf = __bfloat1622float2(hp);
-        const __nv_bfloat162 lp = __floats2bfloat162_rn(a - hf.x, b - hf.y);
-        h[i] = *reinterpret_cast<const uint32_t*>(&hp);
-        l[i] = *reinterpret_cast<const uint32_t*>(&lp);
+        if (p.fp16) {
+          const float lim = 65504.f;
+          const __half2 hp = __floats2half2_rn(fminf(fmaxf(a, -lim), lim), fminf(fmaxf(b, -lim), lim));
+          const float2 hf = __half22float2(hp);
+          const float ra = (a - hf.x) * kLoScaleFp16, rb = (b - hf.y) * kLoScaleFp16;
+          const __half2 lp = __floats2half2_rn(fminf(fmaxf(ra, -lim), lim), fminf(fmaxf(rb, -lim), lim));
+          h[i] = *reinterpret_cast<const uint32_t*>(&hp);
+          l[i] = *reinterpret_cast<const uint32_t*>(&lp);
+        } else {
+          const __nv_bfloat162 hp = __floats2bfloat162_rn(a, b);
+          const float2 hf = __bfloat1622float2(hp);
+          const __nv_bfloat162 lp = __floats2bfloat162_rn((a - hf.x) * kLoScaleBf16, (b - hf.y) * kLoScaleBf16);
+          h[i] = *reinterpret_cast<const uint32_t*>(&hp);
+          l[i] = *reinterpret_cast<const uint32_t*>(&lp);
+        }
       }
       const int64_t o = ((int64_t)n * p.out_pix + pix) * p.Cp + c0 + q * 8;
       *reinterpret_cast<uint4*>(p.hi + o) = make_uint4(h[0], h[1], h[2], h[3]);
@@ -182,48 +203,149 @@ struct TileGeom {
   int bw, bh, bd, bn;      // box extents (w, h, d, images); bw*bh*bd*bn = rows per box
 };
 
-template <int BN>
+// ------------------------------------------------------------------------------------------------ shared pieces
+constexpr int CHUNK = 8;       // k-blocks per promoted chunk (8 * 64 / 16 = 32 accumulator adds)
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+constexpr int tmem_cols_for(int need) { return need <= 32 ? 32 : need <= 64 ? 64 : need <= 128 ? 128 : need <= 256 ? 256 : 512; }
+
+// barrier block: full[S] | empty[S] | accum | cfull[2] | cdrain[2] | tmem slot
+template <int STAGES>
+struct Bars {
+  uint64_t* base;
+  __device__ uint64_t* full(int s) const { return base + s; }
+  __device__ uint64_t* empty(int s) const { return base + STAGES + s; }
+  __device__ uint64_t* accum() const { return base + 2 * STAGES; }
+  __device__ uint64_t* cfull(int b) const { return base + 2 * STAGES + 1 + b; }
+  __device__ uint64_t* cdrain(int b) const { return base + 2 * STAGES + 3 + b; }
+  __device__ uint32_t* slot() const { return reinterpret_cast<uint32_t*>(base + 2 * STAGES + 5); }
+  __device__ void init() const {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(smem_u32(full(s)), 1);
+      mbar_init(smem_u32(empty(s)), 1);
+    }
+    mbar_init(smem_u32(accum()), 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(smem_u32(cfull(b)), 1);
+      mbar_init(smem_u32(cdrain(b)), 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+};
+
+// The single-thread MMA issue loop shared by the forward and wgrad kernels.
+//   TMEM columns: !PROMOTE: main [0,BN) lo [BN,2BN);  PROMOTE: main0 [0,BN) main1 [BN,2BN) lo [2BN,3BN)
+//   lbo/sbo: descriptor strides; kadv: start-address advance (16-byte units) per UMMA_K = 16 step
+template <int BN, bool PROMOTE, int STAGES, int STAGE_BYTES, int A_BYTES, int B_BYTES>
+__device__ __forceinline__ void mma_issue_loop(uint8_t* smem, const Bars<STAGES>& bars, uint32_t tmem_base, int n_iters,
+                                               int mn_major, uint32_t lbo, uint32_t sbo, uint32_t kadv,
+                                               uint32_t fmt /* 0 = fp16 planes, 1 = bf16 planes */) {
+  const uint32_t id_main = make_idesc(BN, mn_major, fmt, fmt);
+  const uint32_t id_lo1 = id_main, id_lo2 = id_main;
+  const uint32_t lo_col = tmem_base + (PROMOTE ? 2 * BN : BN);
+  int stage = 0;
+  uint32_t phase = 0;
+  for (int it = 0; it < n_iters; ++it) {
+    const int chunk = PROMOTE ? it / CHUNK : 0;
+    const bool first = PROMOTE ? (it % CHUNK == 0) : (it == 0);
+    if (PROMOTE && first && chunk >= 2) {        // the epilogue must have drained this region (chunk - 2)
+      mbar_wait(smem_u32(bars.cdrain(chunk & 1)), (uint32_t)(((chunk >> 1) - 1) & 1));
+      tc_fence_after();
+    }
+    mbar_wait(smem_u32(bars.full(stage)), phase);
+    tc_fence_after();
+    const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+    const uint64_t a_hi = make_desc(sa, lbo, sbo), a_lo = make_desc(sa + A_BYTES, lbo, sbo);
+    const uint64_t b_hi = make_desc(sa + 2 * A_BYTES, lbo, sbo), b_lo = make_desc(sa + 2 * A_BYTES + B_BYTES, lbo, sbo);
+    const uint32_t main_col = tmem_base + (PROMOTE ? (uint32_t)(chunk & 1) * BN : 0u);
+#pragma unroll
+    for (int kk = 0; kk < BKC / 16; ++kk) {
+      const uint64_t adv = (uint64_t)(kk * kadv);
+      mma_f16(main_col, a_hi + adv, b_hi + adv, id_main, !(first && kk == 0));
+      mma_f16(lo_col, a_lo + adv, b_hi + adv, id_lo1, (it | kk) != 0);
+      mma_f16(lo_col, a_hi + adv, b_lo + adv, id_lo2, 1);
+    }
+    mma_commit(smem_u32(bars.empty(stage)));
+    if (PROMOTE && ((it % CHUNK) == CHUNK - 1 || it == n_iters - 1)) mma_commit(smem_u32(bars.cfull(chunk & 1)));
+    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+  }
+  if (!PROMOTE) mma_commit(smem_u32(bars.accum()));
+}
+
+// PROMOTE epilogue: drain every finished chunk of the main accumulator into fp32 registers, then add lo / 256.
+// taddr = tmem_base + (lane quarter << 16).  All 128 epilogue threads call this.
+template <int BN, int STAGES>
+__device__ __forceinline__ void collect_promoted(const Bars<STAGES>& bars, uint32_t taddr, int n_iters, float lo_inv,
+                                                 float* acc) {
+#pragma unroll
+  for (int j = 0; j < BN; ++j) acc[j] = 0.f;
+  const int n_chunks = (n_iters + CHUNK - 1) / CHUNK;
+  for (int c = 0; c < n_chunks; ++c) {
+    mbar_wait(smem_u32(bars.cfull(c & 1)), (uint32_t)((c >> 1) & 1));
+    tc_fence_after();
+#pragma unroll
+    for (int cb = 0; cb < BN; cb += 32) {
+      uint32_t r[32];
+      tmem_ld32(taddr + (uint32_t)(c & 1) * BN + cb, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) acc[cb + j] += __uint_as_float(r[j]);
+    }
+    tc_fence_before();
+    mbar_arrive(smem_u32(bars.cdrain(c & 1)));
+  }
+  // every MMA (including the cross terms) has completed once the last chunk's commit has fired
+#pragma unroll
+  for (int cb = 0; cb < BN; cb += 32) {
+    uint32_t r[32];
+    tmem_ld32(taddr + 2 * BN + cb, r);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc[cb + j] = fmaf(__uint_as_float(r[j]), lo_inv, acc[cb + j]);
+  }
+}
+
+template <int BN, bool PROMOTE>
 struct Cfg {
   static constexpr int A_BYTES = BM * 128;
   static constexpr int B_BYTES = BN * 128;
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
   static constexpr int STAGES = (BN == 256) ? 2 : (BN == 128 ? 3 : 4);
   static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 256;
-  static constexpr int TMEM_COLS = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);   // main | lo
+  static constexpr int TMEM_COLS = tmem_cols_for(PROMOTE ? 3 * BN : 2 * BN);
+  static_assert(!PROMOTE || BN <= 128, "promotion needs three accumulator regions");
 };
 
 struct FwdP {
   ConvP c;
   TileGeom g;
   int CoutP;
+  int fp16;             // operand planes are fp16 (forward values) rather than bf16 (anything with gradients)
+  float lo_inv;         // 1 / scale of the low-order planes
 };
 
-template <int BN>
+template <int BN, bool PROMOTE>
 __global__ void __launch_bounds__(NT, 1)
 conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                     const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                     const FwdP fp) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, PROMOTE>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
-  uint64_t* full_bar = bars;
-  uint64_t* empty_bar = bars + C::STAGES;
-  uint64_t* accum_bar = bars + 2 * C::STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 1);
+  const Bars<C::STAGES> bars{reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES)};
+  uint64_t* full_bar = bars.full(0);
+  uint64_t* empty_bar = bars.empty(0);
+  uint64_t* accum_bar = bars.accum();
+  uint32_t* tmem_slot = bars.slot();
 
   const ConvP& p = fp.c;
   const dvd_conv_desc& d = p.d;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-  if (tid == 0) {
-    for (int s = 0; s < C::STAGES; ++s) {
-      mbar_init(smem_u32(full_bar + s), 1);
-      mbar_init(smem_u32(empty_bar + s), 1);
-    }
-    mbar_init(smem_u32(accum_bar), 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
+  if (tid == 0) bars.init();
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                  "r"((uint32_t)C::TMEM_COLS));
@@ -275,28 +397,9 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
     __syncwarp();
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc = make_idesc(BN, 0);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int it = 0; it < n_iters; ++it) {
-        mbar_wait(smem_u32(full_bar + stage), phase);
-        tc_fence_after();
-        const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
-        const uint64_t a_hi = make_desc(sa, 16, 1024), a_lo = make_desc(sa + C::A_BYTES, 16, 1024);
-        const uint64_t b_hi = make_desc(sa + 2 * C::A_BYTES, 16, 1024);
-        const uint64_t b_lo = make_desc(sa + 2 * C::A_BYTES + C::B_BYTES, 16, 1024);
-#pragma unroll
-        for (int kk = 0; kk < BKC / 16; ++kk) {
-          const uint64_t adv = (uint64_t)(kk * 2);       // 32 bytes along K inside the 128-byte swizzle row
-          const uint32_t acc = (it | kk) != 0;
-          mma_f16(tmem_base, a_hi + adv, b_hi + adv, idesc, acc);
-          mma_f16(tmem_base + BN, a_lo + adv, b_hi + adv, idesc, acc);
-          mma_f16(tmem_base + BN, a_hi + adv, b_lo + adv, idesc, 1);
-        }
-        mma_commit(smem_u32(empty_bar + stage));
-        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
-      }
-      mma_commit(smem_u32(accum_bar));
+      // K-major operands: LBO unused (16), SBO = 1024 (8 rows of 128 B), 32 bytes (2 units) per UMMA_K step
+      mma_issue_loop<BN, PROMOTE, C::STAGES, C::STAGE_BYTES, C::A_BYTES, C::B_BYTES>(
+          smem, bars, tmem_base, n_iters, 0, 16, 1024, 2, fp.fp16 ? 0u : 1u);
     }
     __syncwarp();
   } else {
@@ -323,33 +426,47 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
       }
     }
     const bool lead = blockIdx.z == 0;
-    mbar_wait(smem_u32(accum_bar), 0);
-    tc_fence_after();
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-    for (int cb = 0; cb < BN; cb += 32) {
-      if (n0 + cb >= d.Cout) break;
-      uint32_t r0[32], r1[32];
-      tmem_ld32(taddr + cb, r0);
-      tmem_ld32(taddr + BN + cb, r1);
-      tmem_ld_wait();
-      if (!ok) continue;
+    auto emit = [&](int co, float v) {
+      if (lead) {
+        if (p.bias) v += __ldg(p.bias + co);
+        if (p.res) v += __ldg(p.res + ro + (int64_t)co * d.r_cs);
+      }
+      float* dst = p.y + yo + (int64_t)co * d.y_cs;
+      if (p.atomic_out) {
+        atomicAdd(dst, v);
+      } else {
+        if (d.accumulate) v += *dst;
+        if (d.out_act == 1) v = fmaxf(v, 0.f);
+        else if (d.out_act == 2) v = tanhf(v);
+        *dst = v;
+      }
+    };
+    if constexpr (PROMOTE) {
+      float acc[BN];
+      collect_promoted<BN, C::STAGES>(bars, taddr, n_iters, fp.lo_inv, acc);
+      if (ok) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const int co = n0 + cb + j;
-        if (co >= d.Cout) break;
-        float v = __uint_as_float(r0[j]) + __uint_as_float(r1[j]);
-        if (lead) {
-          if (p.bias) v += __ldg(p.bias + co);
-          if (p.res) v += __ldg(p.res + ro + (int64_t)co * d.r_cs);
+        for (int j = 0; j < BN; ++j) {
+          const int co = n0 + j;
+          if (co < d.Cout) emit(co, acc[j]);
         }
-        float* dst = p.y + yo + (int64_t)co * d.y_cs;
-        if (p.atomic_out) {
-          atomicAdd(dst, v);
-        } else {
-          if (d.accumulate) v += *dst;
-          if (d.out_act == 1) v = fmaxf(v, 0.f);
-          else if (d.out_act == 2) v = tanhf(v);
-          *dst = v;
+      }
+    } else {
+      mbar_wait(smem_u32(accum_bar), 0);
+      tc_fence_after();
+      for (int cb = 0; cb < BN; cb += 32) {
+        if (n0 + cb >= d.Cout) break;
+        uint32_t r0[32], r1[32];
+        tmem_ld32(taddr + cb, r0);
+        tmem_ld32(taddr + BN + cb, r1);
+        tmem_ld_wait();
+        if (!ok) continue;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int co = n0 + cb + j;
+          if (co >= d.Cout) break;
+          emit(co, fmaf(__uint_as_float(r1[j]), fp.lo_inv, __uint_as_float(r0[j])));
         }
       }
     }
@@ -371,42 +488,36 @@ struct WgP {
   int nsplit, per_split;   // pixel range per CTA (multiple of 64)
 };
 
-template <int BN>
+template <int BN, bool PROMOTE>
 struct WCfg {
   static constexpr int A_BYTES = 2 * 64 * 128;           // 128 ci = two 64-wide MN blocks of [64 k][128 B]
   static constexpr int B_BYTES = (BN / 64) * 64 * 128;
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
   static constexpr int STAGES = (BN == 256) ? 2 : (BN == 128 ? 3 : 4);
   static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 256;
-  static constexpr int TMEM_COLS = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
+  static constexpr int TMEM_COLS = tmem_cols_for(PROMOTE ? 3 * BN : 2 * BN);
+  static_assert(!PROMOTE || BN <= 128, "promotion needs three accumulator regions");
 };
 
-template <int BN>
+template <int BN, bool PROMOTE>
 __global__ void __launch_bounds__(NT, 1)
 conv_tma_wgrad_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant__ CUtensorMap tmX_lo,
                       const __grid_constant__ CUtensorMap tmY_hi, const __grid_constant__ CUtensorMap tmY_lo,
                       const WgP wp, float* __restrict__ dwp) {
-  using C = WCfg<BN>;
+  using C = WCfg<BN, PROMOTE>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
-  uint64_t* full_bar = bars;
-  uint64_t* empty_bar = bars + C::STAGES;
-  uint64_t* accum_bar = bars + 2 * C::STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 1);
+  const Bars<C::STAGES> bars{reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES)};
+  uint64_t* full_bar = bars.full(0);
+  uint64_t* empty_bar = bars.empty(0);
+  uint64_t* accum_bar = bars.accum();
+  uint32_t* tmem_slot = bars.slot();
 
   const ConvP& p = wp.c;
   const dvd_conv_desc& d = p.d;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-  if (tid == 0) {
-    for (int s = 0; s < C::STAGES; ++s) {
-      mbar_init(smem_u32(full_bar + s), 1);
-      mbar_init(smem_u32(empty_bar + s), 1);
-    }
-    mbar_init(smem_u32(accum_bar), 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
+  if (tid == 0) bars.init();
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                  "r"((uint32_t)C::TMEM_COLS));
@@ -462,52 +573,47 @@ conv_tma_wgrad_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_c
     __syncwarp();
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc = make_idesc(BN, 1);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int it = 0; it < n_iters; ++it) {
-        mbar_wait(smem_u32(full_bar + stage), phase);
-        tc_fence_after();
-        const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
-        // MN-major: LBO = 8192 (next 64-wide MN block), SBO = 1024 (next 8 k-rows)
-        const uint64_t a_hi = make_desc(sa, 8192, 1024), a_lo = make_desc(sa + C::A_BYTES, 8192, 1024);
-        const uint64_t b_hi = make_desc(sa + 2 * C::A_BYTES, 8192, 1024);
-        const uint64_t b_lo = make_desc(sa + 2 * C::A_BYTES + C::B_BYTES, 8192, 1024);
-#pragma unroll
-        for (int kk = 0; kk < BKC / 16; ++kk) {
-          const uint64_t adv = (uint64_t)(kk * 2048 >> 4);     // 16 k-rows of 128 bytes
-          const uint32_t acc = (it | kk) != 0;
-          mma_f16(tmem_base, a_hi + adv, b_hi + adv, idesc, acc);
-          mma_f16(tmem_base + BN, a_lo + adv, b_hi + adv, idesc, acc);
-          mma_f16(tmem_base + BN, a_hi + adv, b_lo + adv, idesc, 1);
-        }
-        mma_commit(smem_u32(empty_bar + stage));
-        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
-      }
-      mma_commit(smem_u32(accum_bar));
+      // MN-major operands: LBO = 8192 (next 64-wide MN block), SBO = 1024 (next 8 k-rows); one UMMA_K step =
+      // 16 k-rows of 128 B = 2048 B = 128 units.  dY is a gradient, so both operands use bf16 planes.
+      mma_issue_loop<BN, PROMOTE, C::STAGES, C::STAGE_BYTES, C::A_BYTES, C::B_BYTES>(
+          smem, bars, tmem_base, n_iters, 1, 8192, 1024, 128, 1u);
     }
     __syncwarp();
   } else {
     const int q = warp & 3;
     const int ci = ci0 + q * 32 + lane;
     const bool ok = ci < d.Cin;
-    mbar_wait(smem_u32(accum_bar), 0);
-    tc_fence_after();
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-    for (int cb = 0; cb < BN; cb += 32) {
-      if (co0 + cb >= d.Cout) break;
-      uint32_t r0[32], r1[32];
-      tmem_ld32(taddr + cb, r0);
-      tmem_ld32(taddr + BN + cb, r1);
-      tmem_ld_wait();
-      if (!ok) continue;
-      float* dst = dwp + ((int64_t)tap * d.Cin + ci) * d.Cout + co0 + cb;
+    float* dst = dwp + ((int64_t)tap * d.Cin + ci) * d.Cout + co0;
+    if constexpr (PROMOTE) {
+      float acc[BN];
+      collect_promoted<BN, C::STAGES>(bars, taddr, n_iters, 1.f / kLoScaleBf16, acc);
+      if (ok) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        if (co0 + cb + j >= d.Cout) break;
-        const float v = __uint_as_float(r0[j]) + __uint_as_float(r1[j]);
-        if (p.atomic_out) atomicAdd(dst + j, v);
-        else dst[j] = v;
+        for (int j = 0; j < BN; ++j) {
+          if (co0 + j < d.Cout) {
+            if (p.atomic_out) atomicAdd(dst + j, acc[j]);
+            else dst[j] = acc[j];
+          }
+        }
+      }
+    } else {
+      mbar_wait(smem_u32(accum_bar), 0);
+      tc_fence_after();
+      for (int cb = 0; cb < BN; cb += 32) {
+        if (co0 + cb >= d.Cout) break;
+        uint32_t r0[32], r1[32];
+        tmem_ld32(taddr + cb, r0);
+        tmem_ld32(taddr + BN + cb, r1);
+        tmem_ld_wait();
+        if (!ok) continue;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          if (co0 + cb + j >= d.Cout) break;
+          const float v = fmaf(__uint_as_float(r1[j]), 1.f / kLoScaleBf16, __uint_as_float(r0[j]));
+          if (p.atomic_out) atomicAdd(dst + cb + j, v);
+          else dst[cb + j] = v;
+        }
       }
     }
     tc_fence_before();
@@ -615,11 +721,11 @@ struct Scratch {
 };
 
 static int prep_planes(const float* src, int N1, int N2, int C, int Cp, int64_t s1, int64_t s2, int64_t cs, int in_pix,
-                       int out_pix, int W, int HW, int up, int relu, __nv_bfloat16* hi, __nv_bfloat16* lo,
+                       int out_pix, int W, int HW, int up, int relu, int fp16, __nv_bfloat16* hi, __nv_bfloat16* lo,
                        cudaStream_t st) {
   PrepP p;
   p.src = src; p.hi = hi; p.lo = lo; p.N2 = N2; p.C = C; p.Cp = Cp; p.s1 = s1; p.s2 = s2; p.cs = cs;
-  p.in_pix = in_pix; p.out_pix = out_pix; p.W = W; p.HW = HW; p.up = up; p.relu = relu;
+  p.in_pix = in_pix; p.out_pix = out_pix; p.W = W; p.HW = HW; p.up = up; p.relu = relu; p.fp16 = fp16;
   const int N = N1 * N2;
   DVD_CHECK_ARG(N <= 65535 * 64);
   // gridDim.z <= 65535: fold large image counts
@@ -630,28 +736,51 @@ static int prep_planes(const float* src, int N1, int N2, int C, int Cp, int64_t 
   return 0;
 }
 
-template <int BN>
+template <int BN, bool PROMOTE>
 static int launch_fwd(const CUtensorMap* m, const FwdP& fp, dim3 grid, cudaStream_t st) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, PROMOTE>;
   static bool configured = false;
   if (!configured) {
-    DVD_CUDA(cudaFuncSetAttribute(conv_tma_fwd_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    DVD_CUDA(cudaFuncSetAttribute(conv_tma_fwd_kernel<BN, PROMOTE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  C::SMEM));
     configured = true;
   }
-  conv_tma_fwd_kernel<BN><<<grid, NT, C::SMEM, st>>>(m[0], m[1], m[2], m[3], fp);
+  conv_tma_fwd_kernel<BN, PROMOTE><<<grid, NT, C::SMEM, st>>>(m[0], m[1], m[2], m[3], fp);
   return 0;
 }
-template <int BN>
+template <int BN, bool PROMOTE>
 static int launch_wgrad(const CUtensorMap* m, const WgP& wp, float* dwp, dim3 grid, cudaStream_t st) {
-  using C = WCfg<BN>;
+  using C = WCfg<BN, PROMOTE>;
   static bool configured = false;
   if (!configured) {
-    DVD_CUDA(cudaFuncSetAttribute(conv_tma_wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    DVD_CUDA(cudaFuncSetAttribute(conv_tma_wgrad_kernel<BN, PROMOTE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  C::SMEM));
     configured = true;
   }
-  conv_tma_wgrad_kernel<BN><<<grid, NT, C::SMEM, st>>>(m[0], m[1], m[2], m[3], wp, dwp);
+  conv_tma_wgrad_kernel<BN, PROMOTE><<<grid, NT, C::SMEM, st>>>(m[0], m[1], m[2], m[3], wp, dwp);
   return 0;
 }
+
+// accumulator policy: promote (BN <= 128, fp32 register accumulation of 8-k-block chunks) whenever a CTA runs more
+// than PROMOTE_MIN k-blocks; env DVD_TC_PROMOTE=0 disables it (BN = 256 tiles, single TMEM accumulator).
+static bool promote_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DVD_TC_PROMOTE");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
+// env DVD_TC_FMT=bf16 forces bf16 planes everywhere (default: fp16 planes for forward convolutions)
+static bool lo_fp16_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DVD_TC_FMT");
+    v = (e && strcmp(e, "bf16") == 0) ? 0 : 1;
+  }
+  return v != 0;
+}
+constexpr int PROMOTE_MIN = 16;
 
 }  // namespace tma
 
@@ -681,13 +810,17 @@ int tma_fwd_launch(ConvP& p, cudaStream_t st) {
   const int N = d.N1 * d.N2;
   FwdP fp;
   if (!tile_geom(128, N, d.D, d.H, d.W, &fp.g)) return fail("internal: geometry%s (%s:%d)", "", __FILE__, __LINE__);
-  int bn = d.Cout >= 256 ? 256 : (d.Cout >= 128 ? 128 : 64);
-  const int mt = ceil_div(p.M, BM);
-  if (bn == 256 && (int64_t)mt * ceil_div(d.Cout, 256) < nsm) bn = 128;
-  const int CinP = round_up(d.Cin, 64), CoutP = round_up(d.Cout, bn);
-  fp.CoutP = CoutP;
+  const int CinP = round_up(d.Cin, 64);
   p.ck = CinP / 64;
   p.iters_total = p.taps * p.ck;
+  const bool promote = promote_enabled() && p.iters_total > PROMOTE_MIN;
+  int bn = d.Cout >= 256 ? 256 : (d.Cout >= 128 ? 128 : 64);
+  const int mt = ceil_div(p.M, BM);
+  if (bn == 256 && (promote || (int64_t)mt * ceil_div(d.Cout, 256) < nsm)) bn = 128;
+  const int CoutP = round_up(d.Cout, bn);
+  fp.CoutP = CoutP;
+  fp.fp16 = (lo_fp16_enabled() && d.x_kind == 1) ? 1 : 0;
+  fp.lo_inv = fp.fp16 ? 1.f / kLoScaleFp16 : 1.f / kLoScaleBf16;
   const int64_t ctas = (int64_t)mt * ceil_div(d.Cout, bn);
   int nsplit = 1;
   if (ctas < nsm && d.out_act == 0 && p.iters_total >= 8) {
@@ -715,10 +848,10 @@ int tma_fwd_launch(ConvP& p, cudaStream_t st) {
   __nv_bfloat16* w_hi = a_lo + a_elems;
   __nv_bfloat16* w_lo = w_hi + w_elems;
   DVD_TRY(prep_planes(p.x, d.N1, d.N2, d.Cin, CinP, d.x_s1, d.x_s2, d.x_cs, p.DHW, p.DHW, d.W, p.HW, d.in_up,
-                      d.in_relu, a_hi, a_lo, st));
+                      d.in_relu, fp.fp16, a_hi, a_lo, st));
   // weights: [tap][Cin][Cout] fp32 -> [tap][CoutP][CinP]   (image = tap, channel = cin, pixel = cout)
   DVD_TRY(prep_planes(p.w, p.taps, 1, d.Cin, CinP, (int64_t)d.Cin * d.Cout, 0, d.Cout, d.Cout, CoutP, 1, 1, 0, 0,
-                      w_hi, w_lo, st));
+                      fp.fp16, w_hi, w_lo, st));
   CUtensorMap maps[4];
   DVD_TRY(make_act_map(&maps[0], a_hi, N, d.D, d.H, d.W, CinP, fp.g));
   DVD_TRY(make_act_map(&maps[1], a_lo, N, d.D, d.H, d.W, CinP, fp.g));
@@ -728,9 +861,9 @@ int tma_fwd_launch(ConvP& p, cudaStream_t st) {
   dim3 grid(mt, ceil_div(d.Cout, bn), nsplit);
   prof_begin(0, 2.0 * p.M * (double)d.Cout * d.Cin * p.taps, st);
   int rc;
-  if (bn == 256) rc = launch_fwd<256>(maps, fp, grid, st);
-  else if (bn == 128) rc = launch_fwd<128>(maps, fp, grid, st);
-  else rc = launch_fwd<64>(maps, fp, grid, st);
+  if (bn == 256) rc = launch_fwd<256, false>(maps, fp, grid, st);
+  else if (bn == 128) rc = promote ? launch_fwd<128, true>(maps, fp, grid, st) : launch_fwd<128, false>(maps, fp, grid, st);
+  else rc = promote ? launch_fwd<64, true>(maps, fp, grid, st) : launch_fwd<64, false>(maps, fp, grid, st);
   prof_end(0, st);
   if (rc) return rc;
   DVD_LAUNCH_CHECK();
@@ -754,7 +887,8 @@ int tma_wgrad_launch(ConvP& p, float* dwp, cudaStream_t st) {
   const int N = d.N1 * d.N2;
   WgP wp;
   if (!tile_geom(64, N, d.D, d.H, d.W, &wp.g)) return fail("internal: geometry%s (%s:%d)", "", __FILE__, __LINE__);
-  const int bn = d.Cout >= 256 ? 256 : (d.Cout >= 128 ? 128 : 64);
+  const bool promote = promote_enabled();        // k = pixels: every CTA runs hundreds of k-blocks
+  const int bn = (d.Cout >= 256 && !promote) ? 256 : (d.Cout >= 128 ? 128 : 64);
   const int64_t base = (int64_t)ceil_div(d.Cin, BM) * ceil_div(d.Cout, bn) * p.taps;
   int nsplit = 1;
   if (base < 2 * nsm) {
@@ -780,8 +914,8 @@ int tma_wgrad_launch(ConvP& p, float* dwp, cudaStream_t st) {
   __nv_bfloat16* y_hi = x_lo + x_elems;
   __nv_bfloat16* y_lo = y_hi + y_elems;
   DVD_TRY(prep_planes(p.x, d.N1, d.N2, d.Cin, CinP, d.x_s1, d.x_s2, d.x_cs, p.DHW, p.DHW, d.W, p.HW, 0, d.in_relu,
-                      x_hi, x_lo, st));
-  DVD_TRY(prep_planes(p.y, d.N1, d.N2, d.Cout, CoutP, d.y_s1, d.y_s2, d.y_cs, p.DHW, p.DHW, d.W, p.HW, 0, 0, y_hi,
+                      0, x_hi, x_lo, st));
+  DVD_TRY(prep_planes(p.y, d.N1, d.N2, d.Cout, CoutP, d.y_s1, d.y_s2, d.y_cs, p.DHW, p.DHW, d.W, p.HW, 0, 0, 0, y_hi,
                       y_lo, st));
   CUtensorMap maps[4];
   DVD_TRY(make_act_map(&maps[0], x_hi, N, d.D, d.H, d.W, CinP, wp.g));
@@ -792,9 +926,10 @@ int tma_wgrad_launch(ConvP& p, float* dwp, cudaStream_t st) {
   dim3 grid(ceil_div(d.Cin, BM), ceil_div(d.Cout, bn), p.taps * nsplit);
   prof_begin(1, 2.0 * p.M * (double)d.Cout * d.Cin * p.taps, st);
   int rc;
-  if (bn == 256) rc = launch_wgrad<256>(maps, wp, dwp, grid, st);
-  else if (bn == 128) rc = launch_wgrad<128>(maps, wp, dwp, grid, st);
-  else rc = launch_wgrad<64>(maps, wp, dwp, grid, st);
+  if (bn == 256) rc = launch_wgrad<256, false>(maps, wp, dwp, grid, st);
+  else if (bn == 128) rc = promote ? launch_wgrad<128, true>(maps, wp, dwp, grid, st)
+                                   : launch_wgrad<128, false>(maps, wp, dwp, grid, st);
+  else rc = promote ? launch_wgrad<64, true>(maps, wp, dwp, grid, st) : launch_wgrad<64, false>(maps, wp, dwp, grid, st);
   prof_end(1, st);
   if (rc) return rc;
   DVD_LAUNCH_CHECK();

@@ -156,7 +156,7 @@ extern "C" int dvd_convgru_layer_fwd(const float* x, int64_t x_bs, int64_t x_ts,
   const int64_t g_ts = 3 * chw, g_bs = (int64_t)T * g_ts, h_ts = chw, h_bs = (int64_t)T * chw;
   // x-halves of all gates, all frames: one implicit GEMM
   {
-    dvd_conv_desc d = base_desc(B, T, Cx, 3 * Ch, H, W, k);
+    dvd_conv_desc d = base_desc(B, T, Cx, 3 * Ch, H, W, k); d.x_kind = 1;
     d.x_s1 = x_bs; d.x_s2 = x_ts; d.y_s1 = g_bs; d.y_s2 = g_ts;
     DVD_TRY(dvd_conv_fwd(&d, x, ws.wx, ws.bias, nullptr, gates, stream));
   }
@@ -167,14 +167,14 @@ extern "C" int dvd_convgru_layer_fwd(const float* x, int64_t x_bs, int64_t x_ts,
     float* g_t = gates + (int64_t)t * g_ts;
     float* rh_t = rh + (int64_t)t * h_ts;
     if (hp) {
-      dvd_conv_desc d = base_desc(B, 1, Ch, 2 * Ch, H, W, k);
+      dvd_conv_desc d = base_desc(B, 1, Ch, 2 * Ch, H, W, k); d.x_kind = 1;
       d.x_s1 = hp_bs; d.y_s1 = g_bs; d.accumulate = 1;
       DVD_TRY(dvd_conv_fwd(&d, hp, ws.whur, nullptr, nullptr, g_t, stream));
     }
     gru_gate_ur_kernel<<<eb, 256, 0, st>>>(g_t, g_bs, hp, hp_bs, rh_t, h_bs, B, chw);
     DVD_LAUNCH_CHECK();
     if (hp) {
-      dvd_conv_desc d = base_desc(B, 1, Ch, Ch, H, W, k);
+      dvd_conv_desc d = base_desc(B, 1, Ch, Ch, H, W, k); d.x_kind = 1;
       d.x_s1 = h_bs; d.y_s1 = g_bs; d.accumulate = 1;
       DVD_TRY(dvd_conv_fwd(&d, rh_t, ws.who, nullptr, nullptr, g_t + 2 * chw, stream));
     }
@@ -240,7 +240,7 @@ extern "C" int dvd_convgru_layer_bwd(const float* x, int64_t x_bs, int64_t x_ts,
   }
   // weight gradients, batched over time
   {
-    dvd_conv_desc d = base_desc(B, T, Cx, 3 * Ch, H, W, k);
+    dvd_conv_desc d = base_desc(B, T, Cx, 3 * Ch, H, W, k); d.x_kind = 1;
     d.x_s1 = x_bs; d.x_s2 = x_ts; d.y_s1 = g_bs; d.y_s2 = g_ts;
     DVD_TRY(dvd_conv_wgrad(&d, x, gates, ws.dwx, stream));
   }
@@ -248,12 +248,13 @@ extern "C" int dvd_convgru_layer_bwd(const float* x, int64_t x_bs, int64_t x_ts,
     bool have = false;
     if (T > 1) {
       dvd_conv_desc d = base_desc(B, T - 1, Ch, 2 * Ch, H, W, k);   // pairs (h_{t-1}, da_t), t = 1..T-1
+      d.x_kind = 1;
       d.x_s1 = h_bs; d.x_s2 = h_ts; d.y_s1 = g_bs; d.y_s2 = g_ts;
       DVD_TRY(dvd_conv_wgrad(&d, h, gates + g_ts, ws.dwhur, stream));
       have = true;
     }
     if (h0) {
-      dvd_conv_desc d = base_desc(B, 1, Ch, 2 * Ch, H, W, k);
+      dvd_conv_desc d = base_desc(B, 1, Ch, 2 * Ch, H, W, k); d.x_kind = 1;
       d.x_s1 = chw; d.y_s1 = g_bs; d.accumulate = have ? 1 : 0;
       DVD_TRY(dvd_conv_wgrad(&d, h0, gates, ws.dwhur, stream));
       have = true;
@@ -262,6 +263,7 @@ extern "C" int dvd_convgru_layer_bwd(const float* x, int64_t x_bs, int64_t x_ts,
   }
   {
     dvd_conv_desc d = base_desc(B, T, Ch, Ch, H, W, k);             // pairs (rh_t, da_o,t)
+    d.x_kind = 1;
     d.x_s1 = h_bs; d.x_s2 = h_ts; d.y_s1 = g_bs; d.y_s2 = g_ts;
     DVD_TRY(dvd_conv_wgrad(&d, rh, gates + 2 * chw, ws.dwho, stream));
   }

@@ -82,8 +82,9 @@ def unpack_wgrad(dwp, like_w):
     return g
 
 
-def _desc(N, Cin, Cout, D, H, W, k, *, in_relu=0, in_up=0, accumulate=0, out_act=0, res_up=0):
+def _desc(N, Cin, Cout, D, H, W, k, *, in_relu=0, in_up=0, accumulate=0, out_act=0, res_up=0, x_kind=0):
     d = ConvDesc()
+    d.x_kind = x_kind
     d.N1, d.N2, d.Cin, d.Cout = N, 1, Cin, Cout
     d.D, d.H, d.W = D, H, W
     d.kD, d.kH, d.kW = k
@@ -101,12 +102,13 @@ def _desc(N, Cin, Cout, D, H, W, k, *, in_relu=0, in_up=0, accumulate=0, out_act
     return d
 
 
-def conv_raw(x, wp, bias, Cout, k, *, in_relu=0, in_up=0, out_act=0, res=None, res_up=0, out=None, accumulate=0):
+def conv_raw(x, wp, bias, Cout, k, *, in_relu=0, in_up=0, out_act=0, res=None, res_up=0, out=None, accumulate=0,
+             x_kind=0):
     """x (N,Cin,[D,]Hs,Ws) contiguous -> y (N,Cout,[D,]H,W) with H = Hs << in_up."""
     N, Cin, D, Hs, Ws = _spatial(x)
     H, W = Hs << in_up, Ws << in_up
     d = _desc(N, Cin, Cout, D, H, W, k, in_relu=in_relu, in_up=in_up, accumulate=accumulate, out_act=out_act,
-              res_up=res_up)
+              res_up=res_up, x_kind=x_kind)
     if out is None:
         shape = (N, Cout, H, W) if x.dim() == 4 else (N, Cout, D, H, W)
         out = _new(shape, x)
@@ -119,7 +121,7 @@ def wgrad_raw(x, dy, k, *, in_relu=0, in_up=0):
     N, Cin, D, Hs, Ws = _spatial(x)
     Cout = dy.shape[1]
     H, W = Hs << in_up, Ws << in_up
-    d = _desc(N, Cin, Cout, D, H, W, k, in_relu=in_relu, in_up=in_up)
+    d = _desc(N, Cin, Cout, D, H, W, k, in_relu=in_relu, in_up=in_up, x_kind=1)
     dwp = _new((k[0] * k[1] * k[2], Cin, Cout), x)
     call("dvd_conv_wgrad", ctypes.byref(d), ptr(x), ptr(dy), ptr(dwp))
     return dwp
@@ -208,7 +210,7 @@ class ConvFn(torch.autograd.Function):
         if res is not None:
             rin = _c(res)
         y = conv_raw(xin, wp, bias, w.shape[0], k, in_relu=in_relu, in_up=in_up, out_act=out_act, res=rin,
-                     res_up=res_up)
+                     res_up=res_up, x_kind=1)
         if lin:
             y = y.view(y.shape[0], y.shape[1])
         ctx.save_for_backward(x, w, sigma if sn else None, u, v, y if out_act else None)

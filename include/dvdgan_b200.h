@@ -55,6 +55,8 @@ typedef struct {
   int out_act;                /* 0 none, 1 relu, 2 tanh (applied after bias / residual) */
   int res_up;                 /* residual is read at (h>>res_up, w>>res_up) */
   int64_t r_s1, r_s2, r_cs;   /* residual strides (if res != NULL) */
+  int x_kind;                 /* tensor-core path hint: 1 = x holds forward activations (O(1e-4..1e4) magnitudes:
+                                 the low-order split plane may be fp16), 0 = x may hold gradients (bf16 plane) */
 } dvd_conv_desc;
 
 int dvd_conv_fwd(const dvd_conv_desc* d, const float* x, const float* w_packed, const float* bias,

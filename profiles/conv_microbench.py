@@ -62,8 +62,12 @@ def main():
             y = ops.conv_raw(x, wp, None, Co, (1, k, k))
             ref = F.conv2d(x[:2].double().cpu(), w.double().cpu(), padding=k // 2)
             e = float((y[:2].double().cpu() - ref).norm() / ref.norm())
-            g = ops.wgrad_raw(x[:4], dy[:4], (1, k, k)) if N * H * W >= 4096 else None
             line += f"   fwd rel-L2 vs fp64: {e:.2e}"
+            nb = max(4, 4096 // (H * W))
+            if nb <= N and Ci * Co * k * k <= 4e6:
+                g = ops.unpack_wgrad(ops.wgrad_raw(x[:nb].contiguous(), dy[:nb].contiguous(), (1, k, k)), w)
+                gref = torch.nn.grad.conv2d_weight(x[:nb].double().cpu(), w.shape, dy[:nb].double().cpu(), padding=k // 2)
+                line += f"  wgrad: {float((g.double().cpu() - gref).norm() / gref.norm()):.2e}"
         print(line, flush=True)
 
 
