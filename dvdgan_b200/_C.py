@@ -29,6 +29,7 @@ _SIGS = {
     "dvd_abi_version": (c_int, []),
     "dvd_launch_count": (ctypes.c_longlong, []),
     "dvd_prof_enable": (I, [I]),
+    "dvd_prof_dump": (I, [ctypes.c_char_p]),
     "dvd_prof_read": (I, [I, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
                           ctypes.POINTER(ctypes.c_longlong)]),
     "dvd_conv_fwd": (I, [ctypes.POINTER(ConvDesc), P, P, P, P, P, P]),

@@ -16,6 +16,7 @@ extern std::atomic<long long> g_launches;   // kernels launched by this library 
 // Optional CUDA-event profiling of the dense engines (category 0: conv fwd/dgrad, 1: wgrad).
 void prof_begin(int category, double flops, cudaStream_t st);
 void prof_end(int category, cudaStream_t st);
+void prof_tag(const char* fmt, int a = 0, int b = 0, int c = 0, int d = 0, int e = 0, int f = 0);   // label of the next record
 
 inline int fail(const char* fmt, const char* a = "", const char* file = "", int line = 0) {
   snprintf(g_last_error, sizeof(g_last_error), fmt, a, file, line);

@@ -5,6 +5,9 @@
 // GEMM view of the forward:  Y[m][co] = sum_{tap, ci} X[m shifted by tap][ci] * Wp[tap][ci][co]
 //   m = output pixel (image, d, h, w)   -- contiguous in NC(D)HW => coalesced gathers and stores
 //   K order = (tap outer, ci inner)     -- the tap's shift / zero-padding predicate is hoisted
+#include <string>
+#include <vector>
+
 #include "common.cuh"
 #include "conv_params.cuh"
 
@@ -313,6 +316,7 @@ static void fill_common(ConvP& p, const dvd_conv_desc* d) {
 template <int BM, int BN, int TM, int TN>
 static int launch_fwd(ConvP& p, cudaStream_t st) {
   dim3 grid(ceil_div(p.M, BM), ceil_div(p.d.Cout, BN), p.nsplit);
+  prof_tag("simt fwd M%d Ci%d Co%d t%d", p.M, p.d.Cin, p.d.Cout, p.taps);
   prof_begin(0, 2.0 * p.M * (double)p.d.Cout * p.d.Cin * p.taps, st);
   conv_fwd_kernel<BM, BN, TM, TN><<<grid, 256, 0, st>>>(p);
   prof_end(0, st);
@@ -535,6 +539,7 @@ extern "C" int dvd_conv_wgrad(const dvd_conv_desc* d, const float* x, const floa
   if (nsplit > 1 && !d->accumulate)
     DVD_CUDA(cudaMemsetAsync(dwp, 0, sizeof(float) * (size_t)p.taps * d->Cin * d->Cout, st));
   dim3 grid(ceil_div(d->Cin, bc), ceil_div(d->Cout, bo), p.taps * nsplit);
+  prof_tag("simt wgrad M%d Ci%d Co%d t%d", p.M, d->Cin, d->Cout, p.taps);
   prof_begin(1, 2.0 * p.M * (double)d->Cout * d->Cin * p.taps, st);
   if (small) conv_wgrad_kernel<64, 64><<<grid, 256, 0, st>>>(p, dwp, nsplit, pps, atomic_out);
   else conv_wgrad_kernel<128, 128><<<grid, 256, 0, st>>>(p, dwp, nsplit, pps, atomic_out);
@@ -712,12 +717,14 @@ extern "C" int dvd_bgemm(int transA, int transB, int M, int N, int K, float alph
 namespace dvd {
 std::atomic<long long> g_launches{0};
 namespace {
-struct ProfRec { cudaEvent_t a, b; double flops; };
+struct ProfRec { cudaEvent_t a, b; double flops; char tag[56]; };
+thread_local char g_prof_tag[56] = "";
 std::mutex g_prof_mu;
 bool g_prof_on = false;
-std::vector<ProfRec> g_prof[2];
+constexpr int kProfCats = 3;       // 0: conv fwd/dgrad GEMM, 1: wgrad GEMM, 2: operand-plane preparation
+std::vector<ProfRec> g_prof[kProfCats];
 std::vector<ProfRec> g_pool;       // recycled event pairs
-long long g_prof_dropped[2] = {0, 0};
+long long g_prof_dropped[kProfCats] = {0, 0, 0};
 constexpr size_t kProfMax = 1 << 16;
 }  // namespace
 
@@ -729,8 +736,13 @@ void prof_begin(int cat, double flops, cudaStream_t st) {
   if (!g_pool.empty()) { r = g_pool.back(); g_pool.pop_back(); }
   else if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
   r.flops = flops;
+  memcpy(r.tag, g_prof_tag, sizeof(r.tag));
   cudaEventRecord(r.a, st);
   g_prof[cat].push_back(r);
+}
+void prof_tag(const char* fmt, int a, int b, int c, int d, int e, int f) {
+  if (!g_prof_on) return;
+  snprintf(g_prof_tag, sizeof(g_prof_tag), fmt, a, b, c, d, e, f);
 }
 void prof_end(int cat, cudaStream_t st) {
   if (!g_prof_on) return;
@@ -749,7 +761,7 @@ extern "C" int dvd_prof_enable(int on) {
 }
 
 extern "C" int dvd_prof_read(int category, double* ms, double* flops, long long* launches) {
-  DVD_CHECK_ARG(category == 0 || category == 1);
+  DVD_CHECK_ARG(category >= 0 && category < dvd::kProfCats);
   DVD_CHECK_ARG(ms && flops && launches);
   std::lock_guard<std::mutex> lk(dvd::g_prof_mu);
   double t = 0.0, f = 0.0;
@@ -766,6 +778,32 @@ extern "C" int dvd_prof_read(int category, double* ms, double* flops, long long*
   *launches = (long long)dvd::g_prof[category].size() + dvd::g_prof_dropped[category];
   dvd::g_prof[category].clear();
   dvd::g_prof_dropped[category] = 0;
+  return 0;
+}
+
+// per-shape table of the recorded launches (does not clear them): "cat \t tag \t launches \t ms \t flops"
+extern "C" int dvd_prof_dump(const char* path) {
+  DVD_CHECK_ARG(path);
+  std::lock_guard<std::mutex> lk(dvd::g_prof_mu);
+  FILE* f = fopen(path, "w");
+  if (!f) return dvd::fail("cannot open %s (%s:%d)", path, __FILE__, __LINE__);
+  for (int cat = 0; cat < dvd::kProfCats; ++cat) {
+    std::vector<std::string> keys;
+    std::vector<double> ms, fl;
+    std::vector<long long> cnt;
+    for (auto& r : dvd::g_prof[cat]) {
+      if (cudaEventSynchronize(r.b) != cudaSuccess) continue;
+      float e = 0.f;
+      if (cudaEventElapsedTime(&e, r.a, r.b) != cudaSuccess) continue;
+      size_t i = 0;
+      for (; i < keys.size(); ++i) if (keys[i] == r.tag) break;
+      if (i == keys.size()) { keys.push_back(r.tag); ms.push_back(0); fl.push_back(0); cnt.push_back(0); }
+      ms[i] += e; fl[i] += r.flops; cnt[i] += 1;
+    }
+    for (size_t i = 0; i < keys.size(); ++i)
+      fprintf(f, "%d\t%s\t%lld\t%.4f\t%.6g\n", cat, keys[i].c_str(), cnt[i], ms[i], fl[i]);
+  }
+  fclose(f);
   return 0;
 }
 

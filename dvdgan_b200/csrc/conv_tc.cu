@@ -498,6 +498,7 @@ int tc_fwd_launch(ConvP& p, cudaStream_t st) {
   p.atomic_out = nsplit > 1;
   if (p.atomic_out && !d.accumulate) DVD_TRY(zero_output_view(p, st));
   dim3 grid(mt, ceil_div(d.Cout, bn), nsplit);
+  prof_tag("tc1 fwd M%d Ci%d Co%d t%d", p.M, d.Cin, d.Cout, p.taps);
   prof_begin(0, 2.0 * p.M * (double)d.Cout * d.Cin * p.taps, st);
   int rc;
   if (bn == 256) rc = tc::launch<256, 0>(p, nullptr, grid, nsplit, per, st);
@@ -533,6 +534,7 @@ int tc_wgrad_launch(ConvP& p, float* dwp, cudaStream_t st) {
   if (nsplit > 1 && !d.accumulate)
     DVD_CUDA(cudaMemsetAsync(dwp, 0, sizeof(float) * (size_t)p.taps * d.Cin * d.Cout, st));
   dim3 grid(ceil_div(d.Cin, tc::BM), ceil_div(d.Cout, bn), p.taps * nsplit);
+  prof_tag("tc1 wgrad M%d Ci%d Co%d t%d", p.M, d.Cin, d.Cout, p.taps);
   prof_begin(1, 2.0 * p.M * (double)d.Cout * d.Cin * p.taps, st);
   int rc;
   if (bn == 256) rc = tc::launch<256, 1>(p, dwp, grid, nsplit, per, st);

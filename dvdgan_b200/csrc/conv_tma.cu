@@ -73,6 +73,65 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm,
       : "memory");
 }
 
+// multicast variants: the box lands at the same CTA-relative offset of every CTA in `mask`, and each of those
+// CTAs' mbarrier (same offset) receives the complete_tx
+__device__ __forceinline__ void tma_load_5d_mc(uint32_t dst, const CUtensorMap* tm, uint32_t bar, uint16_t mask, int c0,
+                                               int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%4, %5, %6, %7, %8}], [%2], %3;"
+      ::"r"(dst), "l"(tm), "r"(bar), "h"(mask), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* tm, uint32_t bar, uint16_t mask, int c0,
+                                               int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%4, %5}], [%2], %3;"
+      ::"r"(dst), "l"(tm), "r"(bar), "h"(mask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctaid_x() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctaid.x;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_ctaid_y() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctaid.y;" : "=r"(r));
+  return r;
+}
+
+// ---- CTA pair (cta_group::2): the two CTAs of a (2,1,1) cluster run one M = 256 MMA; rank 0 issues it
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {      // same offset in CTA `rank`
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+// loads into THIS CTA's shared memory, complete_tx on a barrier that may live in the peer CTA
+__device__ __forceinline__ void tma_load_5d_pair(uint32_t dst, const CUtensorMap* tm, uint32_t bar_cluster, int c0,
+                                                 int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(tm), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* tm, uint32_t bar_cluster, int c0,
+                                                 int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(tm), "r"(bar_cluster), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
+}
+
 // shared-memory matrix descriptor, SWIZZLE_128B.  K-major: rows at 128 B, SBO = 1024 (8-row group).
 // MN-major: 64 MN elements per 128-B row, 8 k-rows per 1024-B atom (SBO), next 64-wide MN block LBO bytes away.
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -86,8 +145,9 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
 }
 // kind::f16 instruction descriptor: D = f32, A/B = bf16 (fmt 1) or fp16 (fmt 0), M = 128, N = n;
 // mn_major: both operands MN-major
-__device__ __forceinline__ uint32_t make_idesc(int n, int mn_major, uint32_t a_fmt = 1, uint32_t b_fmt = 1) {
-  uint32_t d = (1u << 4) | (a_fmt << 7) | (b_fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+__device__ __forceinline__ uint32_t make_idesc(int n, int mn_major, uint32_t a_fmt = 1, uint32_t b_fmt = 1,
+                                               int m = BM) {
+  uint32_t d = (1u << 4) | (a_fmt << 7) | (b_fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
   if (mn_major) d |= (1u << 15) | (1u << 16);
   return d;
 }
@@ -99,8 +159,27 @@ __device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
       : "memory");
 }
+__device__ __forceinline__ void mma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// pair commit: arrives on the barrier at this offset in both CTAs of the pair
+__device__ __forceinline__ void mma_commit_pair(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// commit that arrives on the same barrier offset of every CTA in `mask` (operand stages shared through multicast)
+__device__ __forceinline__ void mma_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(mask) : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
   asm volatile(
@@ -222,15 +301,15 @@ struct Bars {
   __device__ uint64_t* cfull(int b) const { return base + 2 * STAGES + 1 + b; }
   __device__ uint64_t* cdrain(int b) const { return base + 2 * STAGES + 3 + b; }
   __device__ uint32_t* slot() const { return reinterpret_cast<uint32_t*>(base + 2 * STAGES + 5); }
-  __device__ void init() const {
+  __device__ void init(uint32_t empty_count = 1, uint32_t drain_count = 128) const {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(smem_u32(full(s)), 1);
-      mbar_init(smem_u32(empty(s)), 1);
+      mbar_init(smem_u32(empty(s)), empty_count);      // one commit per CTA of the cluster that shares the stage
     }
     mbar_init(smem_u32(accum()), 1);
     for (int b = 0; b < 2; ++b) {
       mbar_init(smem_u32(cfull(b)), 1);
-      mbar_init(smem_u32(cdrain(b)), 128);
+      mbar_init(smem_u32(cdrain(b)), drain_count);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -239,11 +318,12 @@ struct Bars {
 // The single-thread MMA issue loop shared by the forward and wgrad kernels.
 //   TMEM columns: !PROMOTE: main [0,BN) lo [BN,2BN);  PROMOTE: main0 [0,BN) main1 [BN,2BN) lo [2BN,3BN)
 //   lbo/sbo: descriptor strides; kadv: start-address advance (16-byte units) per UMMA_K = 16 step
-template <int BN, bool PROMOTE, int STAGES, int STAGE_BYTES, int A_BYTES, int B_BYTES>
+template <int BN, bool PROMOTE, int STAGES, int STAGE_BYTES, int A_BYTES, int B_BYTES, int CG = 1>
 __device__ __forceinline__ void mma_issue_loop(uint8_t* smem, const Bars<STAGES>& bars, uint32_t tmem_base, int n_iters,
                                                int mn_major, uint32_t lbo, uint32_t sbo, uint32_t kadv,
-                                               uint32_t fmt /* 0 = fp16 planes, 1 = bf16 planes */) {
-  const uint32_t id_main = make_idesc(BN, mn_major, fmt, fmt);
+                                               uint32_t fmt /* 0 = fp16 planes, 1 = bf16 planes */,
+                                               uint16_t commit_mask /* 0: this CTA only */) {
+  const uint32_t id_main = make_idesc(BN, mn_major, fmt, fmt, BM * CG);
   const uint32_t id_lo1 = id_main, id_lo2 = id_main;
   const uint32_t lo_col = tmem_base + (PROMOTE ? 2 * BN : BN);
   int stage = 0;
@@ -264,20 +344,35 @@ __device__ __forceinline__ void mma_issue_loop(uint8_t* smem, const Bars<STAGES>
 #pragma unroll
     for (int kk = 0; kk < BKC / 16; ++kk) {
       const uint64_t adv = (uint64_t)(kk * kadv);
-      mma_f16(main_col, a_hi + adv, b_hi + adv, id_main, !(first && kk == 0));
-      mma_f16(lo_col, a_lo + adv, b_hi + adv, id_lo1, (it | kk) != 0);
-      mma_f16(lo_col, a_hi + adv, b_lo + adv, id_lo2, 1);
+      if constexpr (CG == 2) {
+        mma_f16_pair(main_col, a_hi + adv, b_hi + adv, id_main, !(first && kk == 0));
+        mma_f16_pair(lo_col, a_lo + adv, b_hi + adv, id_lo1, (it | kk) != 0);
+        mma_f16_pair(lo_col, a_hi + adv, b_lo + adv, id_lo2, 1);
+      } else {
+        mma_f16(main_col, a_hi + adv, b_hi + adv, id_main, !(first && kk == 0));
+        mma_f16(lo_col, a_lo + adv, b_hi + adv, id_lo1, (it | kk) != 0);
+        mma_f16(lo_col, a_hi + adv, b_lo + adv, id_lo2, 1);
+      }
     }
-    mma_commit(smem_u32(bars.empty(stage)));
-    if (PROMOTE && ((it % CHUNK) == CHUNK - 1 || it == n_iters - 1)) mma_commit(smem_u32(bars.cfull(chunk & 1)));
+    if constexpr (CG == 2) {
+      mma_commit_pair(smem_u32(bars.empty(stage)));
+      if (PROMOTE && ((it % CHUNK) == CHUNK - 1 || it == n_iters - 1)) mma_commit_pair(smem_u32(bars.cfull(chunk & 1)));
+    } else {
+      if (commit_mask) mma_commit_mc(smem_u32(bars.empty(stage)), commit_mask);
+      else mma_commit(smem_u32(bars.empty(stage)));
+      if (PROMOTE && ((it % CHUNK) == CHUNK - 1 || it == n_iters - 1)) mma_commit(smem_u32(bars.cfull(chunk & 1)));
+    }
     if (++stage == STAGES) { stage = 0; phase ^= 1; }
   }
-  if (!PROMOTE) mma_commit(smem_u32(bars.accum()));
+  if (!PROMOTE) {
+    if constexpr (CG == 2) mma_commit_pair(smem_u32(bars.accum()));
+    else mma_commit(smem_u32(bars.accum()));
+  }
 }
 
 // PROMOTE epilogue: drain every finished chunk of the main accumulator into fp32 registers, then add lo / 256.
 // taddr = tmem_base + (lane quarter << 16).  All 128 epilogue threads call this.
-template <int BN, int STAGES>
+template <int BN, int STAGES, int CG = 1>
 __device__ __forceinline__ void collect_promoted(const Bars<STAGES>& bars, uint32_t taddr, int n_iters, float lo_inv,
                                                  float* acc) {
 #pragma unroll
@@ -295,7 +390,8 @@ __device__ __forceinline__ void collect_promoted(const Bars<STAGES>& bars, uint3
       for (int j = 0; j < 32; ++j) acc[cb + j] += __uint_as_float(r[j]);
     }
     tc_fence_before();
-    mbar_arrive(smem_u32(bars.cdrain(c & 1)));
+    if constexpr (CG == 2) mbar_arrive_cluster(mapa_rank(smem_u32(bars.cdrain(c & 1)), 0));   // the issuer is in rank 0
+    else mbar_arrive(smem_u32(bars.cdrain(c & 1)));
   }
   // every MMA (including the cross terms) has completed once the last chunk's commit has fired
 #pragma unroll
@@ -308,15 +404,21 @@ __device__ __forceinline__ void collect_promoted(const Bars<STAGES>& bars, uint3
   }
 }
 
-template <int BN, bool PROMOTE>
+// CG = 1: one CTA per 128 x BN tile.  CG = 2: a CTA pair (cluster (2,1,1)) per 256 x BN tile: each CTA stages its own
+// 128 rows of A and HALF of the BN weight rows, rank 0 issues tcgen05.mma.cta_group::2 (M = 256) and each CTA's TMEM
+// receives its 128 accumulator rows.  The pair exists because the main loop is bound by the bytes an SM can pull in
+// per cycle (64 KB of planes per 128x128x64 k-block = 3 MMAs per 4 bytes): halving the B bytes per SM is the lever.
+template <int BN, bool PROMOTE, int CG = 1>
 struct Cfg {
   static constexpr int A_BYTES = BM * 128;
-  static constexpr int B_BYTES = BN * 128;
+  static constexpr int B_BYTES = (BN / CG) * 128;
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 2 : (BN == 128 ? 3 : 4);
+  static constexpr int STAGES_FIT = (200 * 1024) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_FIT > 5 ? 5 : STAGES_FIT;
   static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 256;
   static constexpr int TMEM_COLS = tmem_cols_for(PROMOTE ? 3 * BN : 2 * BN);
   static_assert(!PROMOTE || BN <= 128, "promotion needs three accumulator regions");
+  static_assert(STAGES >= 2, "pipeline needs two stages");
 };
 
 struct FwdP {
@@ -325,14 +427,16 @@ struct FwdP {
   int CoutP;
   int fp16;             // operand planes are fp16 (forward values) rather than bf16 (anything with gradients)
   float lo_inv;         // 1 / scale of the low-order planes
+  int cm, cn;           // CG = 1 only: cluster = cm m-tiles x cn n-tiles, the A tile is multicast to the cn CTAs of an
+                        // m-tile (each loads 1/cn of its rows), the B tile to the cm CTAs of an n-tile
 };
 
-template <int BN, bool PROMOTE>
+template <int BN, bool PROMOTE, int CG>
 __global__ void __launch_bounds__(NT, 1)
 conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                     const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                     const FwdP fp) {
-  using C = Cfg<BN, PROMOTE>;
+  using C = Cfg<BN, PROMOTE, CG>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const Bars<C::STAGES> bars{reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES)};
@@ -344,15 +448,26 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
   const ConvP& p = fp.c;
   const dvd_conv_desc& d = p.d;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int cm = CG == 2 ? 1 : fp.cm, cn = CG == 2 ? 1 : fp.cn;
+  const bool clustered = CG == 2 || cm * cn > 1;
+  const uint32_t cx = clustered ? cluster_ctaid_x() : 0u, cy = (clustered && CG == 1) ? cluster_ctaid_y() : 0u;
+  const bool leader = CG == 1 || cx == 0;       // pair: rank 0 owns the full barriers and issues the MMAs
 
-  if (tid == 0) bars.init();
+  if (tid == 0) bars.init(CG == 2 ? 1u : (uint32_t)(cm * cn), CG == 2 ? 256u : 128u);
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"((uint32_t)C::TMEM_COLS));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    if constexpr (CG == 2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "r"((uint32_t)C::TMEM_COLS));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "r"((uint32_t)C::TMEM_COLS));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (clustered) cluster_sync_all();        // peers' barriers are initialised before anything is signalled to them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -364,13 +479,20 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
 
   if (warp == 0) {
     if (lane == 0) {
-      // box origin of this tile: m0 -> (image, z, y, x); the box covers (bn, bd, bh, bw) = 128 rows
-      const int img = m0 / p.DHW;
-      int rem = m0 - img * p.DHW;
+      // box origin of this CTA's slice of the A tile: rows [cy * BM/cn, +BM/cn) of the m-tile -> (image, z, y, x);
+      // the box covers (bn, bd, bh, bw) = BM/cn rows.  B slice: couts [cx * b_rows, +b_rows) of the n-tile.
+      const int a_rows = BM / cn, b_rows = CG == 2 ? BN / 2 : BN / cm;
+      const int ms = m0 + (int)cy * a_rows;
+      const int img = ms / p.DHW;
+      int rem = ms - img * p.DHW;
       const int z0 = rem / p.HW;
       rem -= z0 * p.HW;
       const int y0 = rem / d.W;
       const int x0 = rem - y0 * d.W;
+      const uint32_t a_off = cy * (uint32_t)(a_rows * 128), b_off = CG == 2 ? 0u : cx * (uint32_t)(b_rows * 128);
+      uint16_t mask_a = 0;                                    // same m-tile (cluster x), every n-tile of the cluster
+      for (int y = 0; y < cn; ++y) mask_a |= (uint16_t)(1u << (cx + y * cm));
+      const uint16_t mask_b = (uint16_t)(((1u << cm) - 1u) << (cy * cm));     // same n-tile, every m-tile
       int tap = it_begin / p.ck;
       int cchunk = it_begin - tap * p.ck;
       int stage = 0;
@@ -383,23 +505,45 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
         mbar_wait(smem_u32(empty_bar + stage), phase ^ 1);
         const uint32_t fb = smem_u32(full_bar + stage);
         const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
-        mbar_expect_tx(fb, C::STAGE_BYTES);
         const int c0 = cchunk * BKC;
-        const int cx = x0 + kw - d.kW / 2, cy = y0 + kh - d.kH / 2, cz = z0 + kd - d.kD / 2;
-        tma_load_5d(sa, &tmA_hi, fb, c0, cx, cy, cz, img);
-        tma_load_5d(sa + C::A_BYTES, &tmA_lo, fb, c0, cx, cy, cz, img);
-        tma_load_2d(sa + 2 * C::A_BYTES, &tmB_hi, fb, c0, tap * fp.CoutP + n0);
-        tma_load_2d(sa + 2 * C::A_BYTES + C::B_BYTES, &tmB_lo, fb, c0, tap * fp.CoutP + n0);
+        const int px = x0 + kw - d.kW / 2, py = y0 + kh - d.kH / 2, pz = z0 + kd - d.kD / 2;
+        const int brow = tap * fp.CoutP + n0 + (int)cx * b_rows;
+        if constexpr (CG == 2) {
+          // both CTAs' bytes are counted on rank 0's barrier
+          if (leader) mbar_expect_tx(fb, 2 * C::STAGE_BYTES);
+          const uint32_t fbl = mapa_rank(fb, 0);
+          tma_load_5d_pair(sa, &tmA_hi, fbl, c0, px, py, pz, img);
+          tma_load_5d_pair(sa + C::A_BYTES, &tmA_lo, fbl, c0, px, py, pz, img);
+          tma_load_2d_pair(sa + 2 * C::A_BYTES, &tmB_hi, fbl, c0, brow);
+          tma_load_2d_pair(sa + 2 * C::A_BYTES + C::B_BYTES, &tmB_lo, fbl, c0, brow);
+        } else {
+          mbar_expect_tx(fb, C::STAGE_BYTES);
+          if (cn > 1) {
+            tma_load_5d_mc(sa + a_off, &tmA_hi, fb, mask_a, c0, px, py, pz, img);
+            tma_load_5d_mc(sa + C::A_BYTES + a_off, &tmA_lo, fb, mask_a, c0, px, py, pz, img);
+          } else {
+            tma_load_5d(sa, &tmA_hi, fb, c0, px, py, pz, img);
+            tma_load_5d(sa + C::A_BYTES, &tmA_lo, fb, c0, px, py, pz, img);
+          }
+          if (cm > 1) {
+            tma_load_2d_mc(sa + 2 * C::A_BYTES + b_off, &tmB_hi, fb, mask_b, c0, brow);
+            tma_load_2d_mc(sa + 2 * C::A_BYTES + C::B_BYTES + b_off, &tmB_lo, fb, mask_b, c0, brow);
+          } else {
+            tma_load_2d(sa + 2 * C::A_BYTES, &tmB_hi, fb, c0, brow);
+            tma_load_2d(sa + 2 * C::A_BYTES + C::B_BYTES, &tmB_lo, fb, c0, brow);
+          }
+        }
         if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         if (++cchunk == p.ck) { cchunk = 0; ++tap; }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (lane == 0 && leader) {
       // K-major operands: LBO unused (16), SBO = 1024 (8 rows of 128 B), 32 bytes (2 units) per UMMA_K step
-      mma_issue_loop<BN, PROMOTE, C::STAGES, C::STAGE_BYTES, C::A_BYTES, C::B_BYTES>(
-          smem, bars, tmem_base, n_iters, 0, 16, 1024, 2, fp.fp16 ? 0u : 1u);
+      mma_issue_loop<BN, PROMOTE, C::STAGES, C::STAGE_BYTES, C::A_BYTES, C::B_BYTES, CG>(
+          smem, bars, tmem_base, n_iters, 0, 16, 1024, 2, fp.fp16 ? 0u : 1u,
+          (CG == 1 && clustered) ? (uint16_t)((1u << (cm * cn)) - 1u) : (uint16_t)0);
     }
     __syncwarp();
   } else {
@@ -427,30 +571,50 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
     }
     const bool lead = blockIdx.z == 0;
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-    auto emit = [&](int co, float v) {
-      if (lead) {
-        if (p.bias) v += __ldg(p.bias + co);
-        if (p.res) v += __ldg(p.res + ro + (int64_t)co * d.r_cs);
+    // 32 output channels of this thread's pixel.  Everything that has to be READ (previous value for accumulate,
+    // residual, bias) is fetched for all 32 channels before the first store: a load-add-store chain per channel
+    // would serialise 256 DRAM round trips per tile (measured: +60 % on the per-timestep h-half GEMMs).
+    auto emit32 = [&](int cb, const float* v) {
+      const int co0 = n0 + cb;
+      if (co0 >= d.Cout) return;
+      float add[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) add[j] = 0.f;
+      if (!p.atomic_out && d.accumulate) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (co0 + j < d.Cout) add[j] = __ldcg(p.y + yo + (int64_t)(co0 + j) * d.y_cs);
       }
-      float* dst = p.y + yo + (int64_t)co * d.y_cs;
-      if (p.atomic_out) {
-        atomicAdd(dst, v);
-      } else {
-        if (d.accumulate) v += *dst;
-        if (d.out_act == 1) v = fmaxf(v, 0.f);
-        else if (d.out_act == 2) v = tanhf(v);
-        *dst = v;
+      if (lead && p.res) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (co0 + j < d.Cout) add[j] += __ldg(p.res + ro + (int64_t)(co0 + j) * d.r_cs);
+      }
+      if (lead && p.bias) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (co0 + j < d.Cout) add[j] += __ldg(p.bias + co0 + j);
+      }
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        if (co0 + j >= d.Cout) break;
+        float o = v[j] + add[j];
+        float* dst = p.y + yo + (int64_t)(co0 + j) * d.y_cs;
+        if (p.atomic_out) {
+          atomicAdd(dst, o);
+        } else {
+          if (d.out_act == 1) o = fmaxf(o, 0.f);
+          else if (d.out_act == 2) o = tanhf(o);
+          *dst = o;
+        }
       }
     };
     if constexpr (PROMOTE) {
       float acc[BN];
-      collect_promoted<BN, C::STAGES>(bars, taddr, n_iters, fp.lo_inv, acc);
+      collect_promoted<BN, C::STAGES, CG>(bars, taddr, n_iters, fp.lo_inv, acc);
       if (ok) {
 #pragma unroll
-        for (int j = 0; j < BN; ++j) {
-          const int co = n0 + j;
-          if (co < d.Cout) emit(co, acc[j]);
-        }
+        for (int cb = 0; cb < BN; cb += 32) emit32(cb, acc + cb);
       }
     } else {
       mbar_wait(smem_u32(accum_bar), 0);
@@ -462,21 +626,23 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
         tmem_ld32(taddr + BN + cb, r1);
         tmem_ld_wait();
         if (!ok) continue;
+        float v[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int co = n0 + cb + j;
-          if (co >= d.Cout) break;
-          emit(co, fmaf(__uint_as_float(r1[j]), fp.lo_inv, __uint_as_float(r0[j])));
-        }
+        for (int j = 0; j < 32; ++j) v[j] = fmaf(__uint_as_float(r1[j]), fp.lo_inv, __uint_as_float(r0[j]));
+        emit32(cb, v);
       }
     }
     tc_fence_before();
   }
 
   __syncthreads();
+  if (clustered) cluster_sync_all();        // no CTA leaves while a peer may still signal its barriers / read its smem
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS));
+    if constexpr (CG == 2)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS));
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS));
   }
 }
 
@@ -486,25 +652,30 @@ struct WgP {
   ConvP c;
   TileGeom g;           // box of 64 pixels
   int nsplit, per_split;   // pixel range per CTA (multiple of 64)
+  int cm, cn;              // cluster = cm ci-blocks x cn co-blocks: the dY tile is multicast across cm, the X tile across cn
 };
 
-template <int BN, bool PROMOTE>
+template <int BN, bool PROMOTE, int CG = 1>
 struct WCfg {
   static constexpr int A_BYTES = 2 * 64 * 128;           // 128 ci = two 64-wide MN blocks of [64 k][128 B]
-  static constexpr int B_BYTES = (BN / 64) * 64 * 128;
+  static constexpr int B_BLOCKS = BN / CG / 64;          // 64-wide co blocks staged by this CTA (pair: half of BN)
+  static constexpr int B_BYTES = B_BLOCKS * 64 * 128;
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 2 : (BN == 128 ? 3 : 4);
+  static constexpr int STAGES_FIT = (200 * 1024) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_FIT > 5 ? 5 : STAGES_FIT;
   static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 256;
   static constexpr int TMEM_COLS = tmem_cols_for(PROMOTE ? 3 * BN : 2 * BN);
   static_assert(!PROMOTE || BN <= 128, "promotion needs three accumulator regions");
+  static_assert(BN % (64 * CG) == 0, "whole 64-wide co blocks per CTA");
 };
 
-template <int BN, bool PROMOTE>
+// CG = 2: CTA pair = 256 ci x BN co; each CTA stages its own 128 ci of X and half of the dY blocks.
+template <int BN, bool PROMOTE, int CG>
 __global__ void __launch_bounds__(NT, 1)
 conv_tma_wgrad_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant__ CUtensorMap tmX_lo,
                       const __grid_constant__ CUtensorMap tmY_hi, const __grid_constant__ CUtensorMap tmY_lo,
                       const WgP wp, float* __restrict__ dwp) {
-  using C = WCfg<BN, PROMOTE>;
+  using C = WCfg<BN, PROMOTE, CG>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const Bars<C::STAGES> bars{reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES)};
@@ -516,15 +687,26 @@ conv_tma_wgrad_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_c
   const ConvP& p = wp.c;
   const dvd_conv_desc& d = p.d;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int cm = CG == 2 ? 1 : wp.cm, cn = CG == 2 ? 1 : wp.cn;
+  const bool clustered = CG == 2 || cm * cn > 1;
+  const uint32_t cx = clustered ? cluster_ctaid_x() : 0u, cy = (clustered && CG == 1) ? cluster_ctaid_y() : 0u;
+  const bool leader = CG == 1 || cx == 0;
 
-  if (tid == 0) bars.init();
+  if (tid == 0) bars.init(CG == 2 ? 1u : (uint32_t)(cm * cn), CG == 2 ? 256u : 128u);
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"((uint32_t)C::TMEM_COLS));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    if constexpr (CG == 2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "r"((uint32_t)C::TMEM_COLS));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "r"((uint32_t)C::TMEM_COLS));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (clustered) cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -543,6 +725,9 @@ conv_tma_wgrad_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_c
       const int kh = t2 % d.kH;
       const int kd = t2 / d.kH;
       const int ox = kw - d.kW / 2, oy = kh - d.kH / 2, oz = kd - d.kD / 2;
+      uint16_t mask_a = 0;                                    // same ci-block (cluster x), every co-block of the cluster
+      for (int y = 0; y < cn; ++y) mask_a |= (uint16_t)(1u << (cx + y * cm));
+      const uint16_t mask_b = (uint16_t)(((1u << cm) - 1u) << (cy * cm));     // same co-block, every ci-block
       int stage = 0;
       uint32_t phase = 0;
       for (int it = 0; it < n_iters; ++it) {
@@ -556,27 +741,53 @@ conv_tma_wgrad_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_c
         mbar_wait(smem_u32(empty_bar + stage), phase ^ 1);
         const uint32_t fb = smem_u32(full_bar + stage);
         const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
-        mbar_expect_tx(fb, C::STAGE_BYTES);
+        if constexpr (CG == 2) {
+          if (leader) mbar_expect_tx(fb, 2 * C::STAGE_BYTES);
+          const uint32_t fbl = mapa_rank(fb, 0);
+          const int cob = co0 + (int)cx * (BN / 2);           // this CTA's half of the pair's co range
 #pragma unroll
-        for (int b = 0; b < 2; ++b) {
-          tma_load_5d(sa + b * 8192, &tmX_hi, fb, ci0 + b * 64, x0 + ox, y0 + oy, z0 + oz, img);
-          tma_load_5d(sa + C::A_BYTES + b * 8192, &tmX_lo, fb, ci0 + b * 64, x0 + ox, y0 + oy, z0 + oz, img);
-        }
+          for (int b = 0; b < 2; ++b) {
+            tma_load_5d_pair(sa + b * 8192, &tmX_hi, fbl, ci0 + b * 64, x0 + ox, y0 + oy, z0 + oz, img);
+            tma_load_5d_pair(sa + C::A_BYTES + b * 8192, &tmX_lo, fbl, ci0 + b * 64, x0 + ox, y0 + oy, z0 + oz, img);
+          }
 #pragma unroll
-        for (int b = 0; b < BN / 64; ++b) {
-          tma_load_5d(sa + 2 * C::A_BYTES + b * 8192, &tmY_hi, fb, co0 + b * 64, x0, y0, z0, img);
-          tma_load_5d(sa + 2 * C::A_BYTES + C::B_BYTES + b * 8192, &tmY_lo, fb, co0 + b * 64, x0, y0, z0, img);
+          for (int b = 0; b < C::B_BLOCKS; ++b) {
+            tma_load_5d_pair(sa + 2 * C::A_BYTES + b * 8192, &tmY_hi, fbl, cob + b * 64, x0, y0, z0, img);
+            tma_load_5d_pair(sa + 2 * C::A_BYTES + C::B_BYTES + b * 8192, &tmY_lo, fbl, cob + b * 64, x0, y0, z0, img);
+          }
+        } else {
+          mbar_expect_tx(fb, C::STAGE_BYTES);
+          // each CTA loads 1/cn of the X blocks and 1/cm of the dY blocks and multicasts them to the CTAs sharing them
+          for (int b = (int)cy * (2 / cn); b < ((int)cy + 1) * (2 / cn); ++b) {
+            if (cn > 1) {
+              tma_load_5d_mc(sa + b * 8192, &tmX_hi, fb, mask_a, ci0 + b * 64, x0 + ox, y0 + oy, z0 + oz, img);
+              tma_load_5d_mc(sa + C::A_BYTES + b * 8192, &tmX_lo, fb, mask_a, ci0 + b * 64, x0 + ox, y0 + oy, z0 + oz, img);
+            } else {
+              tma_load_5d(sa + b * 8192, &tmX_hi, fb, ci0 + b * 64, x0 + ox, y0 + oy, z0 + oz, img);
+              tma_load_5d(sa + C::A_BYTES + b * 8192, &tmX_lo, fb, ci0 + b * 64, x0 + ox, y0 + oy, z0 + oz, img);
+            }
+          }
+          for (int b = (int)cx * (C::B_BLOCKS / cm); b < ((int)cx + 1) * (C::B_BLOCKS / cm); ++b) {
+            if (cm > 1) {
+              tma_load_5d_mc(sa + 2 * C::A_BYTES + b * 8192, &tmY_hi, fb, mask_b, co0 + b * 64, x0, y0, z0, img);
+              tma_load_5d_mc(sa + 2 * C::A_BYTES + C::B_BYTES + b * 8192, &tmY_lo, fb, mask_b, co0 + b * 64, x0, y0, z0, img);
+            } else {
+              tma_load_5d(sa + 2 * C::A_BYTES + b * 8192, &tmY_hi, fb, co0 + b * 64, x0, y0, z0, img);
+              tma_load_5d(sa + 2 * C::A_BYTES + C::B_BYTES + b * 8192, &tmY_lo, fb, co0 + b * 64, x0, y0, z0, img);
+            }
+          }
         }
         if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (lane == 0 && leader) {
       // MN-major operands: LBO = 8192 (next 64-wide MN block), SBO = 1024 (next 8 k-rows); one UMMA_K step =
       // 16 k-rows of 128 B = 2048 B = 128 units.  dY is a gradient, so both operands use bf16 planes.
-      mma_issue_loop<BN, PROMOTE, C::STAGES, C::STAGE_BYTES, C::A_BYTES, C::B_BYTES>(
-          smem, bars, tmem_base, n_iters, 1, 8192, 1024, 128, 1u);
+      mma_issue_loop<BN, PROMOTE, C::STAGES, C::STAGE_BYTES, C::A_BYTES, C::B_BYTES, CG>(
+          smem, bars, tmem_base, n_iters, 1, 8192, 1024, 128, 1u,
+          (CG == 1 && clustered) ? (uint16_t)((1u << (cm * cn)) - 1u) : (uint16_t)0);
     }
     __syncwarp();
   } else {
@@ -587,7 +798,7 @@ conv_tma_wgrad_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_c
     float* dst = dwp + ((int64_t)tap * d.Cin + ci) * d.Cout + co0;
     if constexpr (PROMOTE) {
       float acc[BN];
-      collect_promoted<BN, C::STAGES>(bars, taddr, n_iters, 1.f / kLoScaleBf16, acc);
+      collect_promoted<BN, C::STAGES, CG>(bars, taddr, n_iters, 1.f / kLoScaleBf16, acc);
       if (ok) {
 #pragma unroll
         for (int j = 0; j < BN; ++j) {
@@ -620,9 +831,13 @@ conv_tma_wgrad_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_c
   }
 
   __syncthreads();
+  if (clustered) cluster_sync_all();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS));
+    if constexpr (CG == 2)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS));
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS));
   }
 }
 
@@ -676,7 +891,12 @@ static int make_w_map(CUtensorMap* tm, const void* base, int rows, int Cp, int b
 
 // rows consecutive flat pixels (rows = 128 or 64) as a box (bn, bd, bh, bw); false if the geometry does not tile
 static bool tile_geom(int rows, int N, int D, int H, int W, TileGeom* g) {
-  if (W > rows || rows % W) return false;
+  if (W > rows) {                      // a fraction of one image row
+    if (W % rows) return false;
+    g->bw = rows; g->bh = g->bd = g->bn = 1;
+    return true;
+  }
+  if (rows % W) return false;
   g->bw = W;
   int left = rows / W;
   g->bh = H < left ? H : left;
@@ -731,45 +951,87 @@ static int prep_planes(const float* src, int N1, int N2, int C, int Cp, int64_t 
   // gridDim.z <= 65535: fold large image counts
   DVD_CHECK_ARG(N <= 65535);
   dim3 grid(ceil_div(out_pix, 32), Cp / 64, N);
+  prof_tag("prep N%d pix%d C%d", N, out_pix, Cp);
+  prof_begin(2, (double)N * out_pix * Cp * 8.0, st);          // "flops" = bytes moved (4 in + 4 out per element)
   prep_planes_kernel<<<grid, 256, 0, st>>>(p);
+  prof_end(2, st);
   DVD_LAUNCH_CHECK();
   return 0;
 }
 
-template <int BN, bool PROMOTE>
+template <int BN, bool PROMOTE, int CG>
 static int launch_fwd(const CUtensorMap* m, const FwdP& fp, dim3 grid, cudaStream_t st) {
-  using C = Cfg<BN, PROMOTE>;
+  using C = Cfg<BN, PROMOTE, CG>;
   static bool configured = false;
   if (!configured) {
-    DVD_CUDA(cudaFuncSetAttribute(conv_tma_fwd_kernel<BN, PROMOTE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    DVD_CUDA(cudaFuncSetAttribute(conv_tma_fwd_kernel<BN, PROMOTE, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   C::SMEM));
     configured = true;
   }
-  conv_tma_fwd_kernel<BN, PROMOTE><<<grid, NT, C::SMEM, st>>>(m[0], m[1], m[2], m[3], fp);
+  const int cx = CG == 2 ? 2 : fp.cm, cy = CG == 2 ? 1 : fp.cn;
+  if (cx * cy > 1) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = dim3(NT); cfg.dynamicSmemBytes = C::SMEM; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cx; attr[0].val.clusterDim.y = cy; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    DVD_CUDA(cudaLaunchKernelEx(&cfg, conv_tma_fwd_kernel<BN, PROMOTE, CG>, m[0], m[1], m[2], m[3], fp));
+  } else {
+    conv_tma_fwd_kernel<BN, PROMOTE, CG><<<grid, NT, C::SMEM, st>>>(m[0], m[1], m[2], m[3], fp);
+  }
   return 0;
 }
-template <int BN, bool PROMOTE>
+template <int BN, bool PROMOTE, int CG>
 static int launch_wgrad(const CUtensorMap* m, const WgP& wp, float* dwp, dim3 grid, cudaStream_t st) {
-  using C = WCfg<BN, PROMOTE>;
+  using C = WCfg<BN, PROMOTE, CG>;
   static bool configured = false;
   if (!configured) {
-    DVD_CUDA(cudaFuncSetAttribute(conv_tma_wgrad_kernel<BN, PROMOTE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    DVD_CUDA(cudaFuncSetAttribute(conv_tma_wgrad_kernel<BN, PROMOTE, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   C::SMEM));
     configured = true;
   }
-  conv_tma_wgrad_kernel<BN, PROMOTE><<<grid, NT, C::SMEM, st>>>(m[0], m[1], m[2], m[3], wp, dwp);
+  const int cx = CG == 2 ? 2 : wp.cm, cy = CG == 2 ? 1 : wp.cn;
+  if (cx * cy > 1) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = dim3(NT); cfg.dynamicSmemBytes = C::SMEM; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cx; attr[0].val.clusterDim.y = cy; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    DVD_CUDA(cudaLaunchKernelEx(&cfg, conv_tma_wgrad_kernel<BN, PROMOTE, CG>, m[0], m[1], m[2], m[3], wp, dwp));
+  } else {
+    conv_tma_wgrad_kernel<BN, PROMOTE, CG><<<grid, NT, C::SMEM, st>>>(m[0], m[1], m[2], m[3], wp, dwp);
+  }
   return 0;
 }
 
-// accumulator policy: promote (BN <= 128, fp32 register accumulation of 8-k-block chunks) whenever a CTA runs more
-// than PROMOTE_MIN k-blocks; env DVD_TC_PROMOTE=0 disables it (BN = 256 tiles, single TMEM accumulator).
-static bool promote_enabled() {
+// accumulator policy.  The tensor core truncates its fp32 accumulator on every add (a bias of ~K/16 * 2^-25 relative:
+// 1.4e-5 at K = 12800, measured).  With PROMOTE (BN <= 128, three TMEM regions) the main accumulator is drained into
+// fp32 registers every 8 k-blocks; the 192/256-wide tiles that the SM-ingest roofline wants have no TMEM left for it.
+// env DVD_TC_PROMOTE: unset/"auto" = promote only where the tile is <= 128 wide anyway, "1" = always (caps tiles at
+// 128 columns), "0" = never.  Measured at G's output (ch = 32, 48 frames): 1.3e-4 rel-L2 vs the fp32 reference with
+// promotion everywhere, 2.3e-4 without, the reference's own fp32-vs-fp64 error being 1.3e-4 (profiles/).
+static int promote_mode() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("DVD_TC_PROMOTE");
-    v = (e && e[0] == '0') ? 0 : 1;
+    v = (e && e[0] == '0') ? 0 : ((e && e[0] == '1') ? 1 : 2);
   }
-  return v != 0;
+  return v;
+}
+// widest tile with the least padded columns (ties -> wider)
+static int pick_bn(int Cout, int max_bn, bool allow_192) {
+  if (Cout <= 64) return 64;
+  const int cand[3] = {256, 192, 128};
+  int best = 128, best_waste = 1 << 30;
+  for (int i = 0; i < 3; ++i) {
+    const int bn = cand[i];
+    if (bn > max_bn || (bn == 192 && !allow_192)) continue;
+    const int waste = (Cout + bn - 1) / bn * bn - Cout;
+    if (waste < best_waste) { best = bn; best_waste = waste; }
+  }
+  return best;
 }
 // env DVD_TC_FMT=bf16 forces bf16 planes everywhere (default: fp16 planes for forward convolutions)
 static bool lo_fp16_enabled() {
@@ -781,6 +1043,39 @@ static bool lo_fp16_enabled() {
   return v != 0;
 }
 constexpr int PROMOTE_MIN = 16;
+
+// Cluster shape (cm m-tiles x cn n-tiles) for operand multicast.  The main loop is bound by the L2 -> SM fabric
+// (64 KB of operand planes per 128x128x64 k-block at cm = cn = 1, see profiles/); a cm x cn cluster cuts the bytes
+// each CTA pulls from L2 to 32/cn + 32/cm KB.  env DVD_TC_CLUSTER="cm,cn" overrides (1,1 = off).
+static void cluster_override(int* cm, int* cn) {
+  static int ocm = -1, ocn = -1;
+  if (ocm < 0) {
+    ocm = 0; ocn = 0;
+    const char* e = getenv("DVD_TC_CLUSTER");
+    if (e) sscanf(e, "%d,%d", &ocm, &ocn);
+  }
+  if (ocm > 0 && ocn > 0) { *cm = ocm; *cn = ocn; }
+}
+// env DVD_TC_PAIR=0 disables the CTA-pair (cta_group::2) kernels
+static bool pair_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DVD_TC_PAIR");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
+static void pick_cluster(int mt, int nt, int nsm, int* cm, int* cn) {
+  int want_m = 1, want_n = 1;      // measured: multicast alone does not pay (the SM-side ingest is the limit)
+  cluster_override(&want_m, &want_n);
+  int m = 1, n = 1;
+  while (m * 2 <= want_m && mt % (m * 2) == 0) m *= 2;
+  while (n * 2 <= want_n && nt % (n * 2) == 0) n *= 2;
+  if (n < want_n && want_m * want_n >= 4)          // n-tiles do not divide: take the sharing along M instead
+    while (m * 2 <= 4 && m * n * 2 <= want_m * want_n && mt % (m * 2) == 0) m *= 2;
+  if ((int64_t)mt * nt < nsm) { m = 1; n = 1; }    // under one wave: keep every SM busy instead
+  *cm = m; *cn = n;
+}
 
 }  // namespace tma
 
@@ -797,7 +1092,9 @@ static int impl_pref2() {
 bool tma_fwd_eligible(const ConvP& p) {
   if (impl_pref2() != 2) return false;
   const dvd_conv_desc& d = p.d;
-  if (d.Cin < 32 || d.Cout < 64 || p.M < 128) return false;
+  // narrow layers (3-channel image convs) ride the tensor path, zero-padded to one 64-wide block, once there are
+  // enough pixels for the padding not to matter: the SIMT engine runs them at < 1 TFLOP/s
+  if (p.M < 128 || ((d.Cin < 32 || d.Cout < 64) && p.M < (1 << 18))) return false;
   if ((int64_t)d.N1 * d.N2 > 65535) return false;
   tma::TileGeom g;
   return tma::tile_geom(128, d.N1 * d.N2, d.D, d.H, d.W, &g) && tma::get_encode() != nullptr;
@@ -813,10 +1110,11 @@ int tma_fwd_launch(ConvP& p, cudaStream_t st) {
   const int CinP = round_up(d.Cin, 64);
   p.ck = CinP / 64;
   p.iters_total = p.taps * p.ck;
-  const bool promote = promote_enabled() && p.iters_total > PROMOTE_MIN;
-  int bn = d.Cout >= 256 ? 256 : (d.Cout >= 128 ? 128 : 64);
+  const int pmode = promote_mode();
+  int bn = pick_bn(d.Cout, pmode == 1 ? 128 : 256, true);
   const int mt = ceil_div(p.M, BM);
-  if (bn == 256 && (promote || (int64_t)mt * ceil_div(d.Cout, 256) < nsm)) bn = 128;
+  if (bn > 128 && (int64_t)mt * ceil_div(d.Cout, bn) < nsm) bn = 128;        // small grids: more, narrower tiles
+  const bool promote = pmode != 0 && bn <= 128 && p.iters_total > PROMOTE_MIN;
   const int CoutP = round_up(d.Cout, bn);
   fp.CoutP = CoutP;
   fp.fp16 = (lo_fp16_enabled() && d.x_kind == 1) ? 1 : 0;
@@ -853,17 +1151,35 @@ int tma_fwd_launch(ConvP& p, cudaStream_t st) {
   DVD_TRY(prep_planes(p.w, p.taps, 1, d.Cin, CinP, (int64_t)d.Cin * d.Cout, 0, d.Cout, d.Cout, CoutP, 1, 1, 0, 0,
                       fp.fp16, w_hi, w_lo, st));
   CUtensorMap maps[4];
-  DVD_TRY(make_act_map(&maps[0], a_hi, N, d.D, d.H, d.W, CinP, fp.g));
-  DVD_TRY(make_act_map(&maps[1], a_lo, N, d.D, d.H, d.W, CinP, fp.g));
-  DVD_TRY(make_w_map(&maps[2], w_hi, p.taps * CoutP, CinP, bn));
-  DVD_TRY(make_w_map(&maps[3], w_lo, p.taps * CoutP, CinP, bn));
+  // CTA pairs (256 x bn tiles) whenever there is more than one wave of tiles; otherwise optional multicast clusters,
+  // only where the slices are still legal TMA boxes
+  const bool pair = pair_enabled() && mt % 2 == 0 && ctas >= nsm && bn >= 64;
+  fp.cm = fp.cn = 1;
+  if (!pair) pick_cluster(mt, ceil_div(d.Cout, bn), nsm, &fp.cm, &fp.cn);
+  TileGeom ga = fp.g;
+  while (fp.cn > 1 && !tile_geom(BM / fp.cn, N, d.D, d.H, d.W, &ga)) fp.cn >>= 1;
+  if (fp.cn == 1) ga = fp.g;
+  DVD_TRY(make_act_map(&maps[0], a_hi, N, d.D, d.H, d.W, CinP, ga));
+  DVD_TRY(make_act_map(&maps[1], a_lo, N, d.D, d.H, d.W, CinP, ga));
+  DVD_TRY(make_w_map(&maps[2], w_hi, p.taps * CoutP, CinP, pair ? bn / 2 : bn / fp.cm));
+  DVD_TRY(make_w_map(&maps[3], w_lo, p.taps * CoutP, CinP, pair ? bn / 2 : bn / fp.cm));
   fp.c = p;
   dim3 grid(mt, ceil_div(d.Cout, bn), nsplit);
+  prof_tag(pair ? "fwd M%d Ci%d Co%d t%d bn%d pair acc%d" : "fwd M%d Ci%d Co%d t%d bn%d acc%d", p.M, d.Cin, d.Cout,
+           p.taps, bn, d.accumulate + 2 * (nsplit > 1));
   prof_begin(0, 2.0 * p.M * (double)d.Cout * d.Cin * p.taps, st);
   int rc;
-  if (bn == 256) rc = launch_fwd<256, false>(maps, fp, grid, st);
-  else if (bn == 128) rc = promote ? launch_fwd<128, true>(maps, fp, grid, st) : launch_fwd<128, false>(maps, fp, grid, st);
-  else rc = promote ? launch_fwd<64, true>(maps, fp, grid, st) : launch_fwd<64, false>(maps, fp, grid, st);
+  if (pair) {
+    if (bn == 256) rc = launch_fwd<256, false, 2>(maps, fp, grid, st);
+    else if (bn == 192) rc = launch_fwd<192, false, 2>(maps, fp, grid, st);
+    else if (bn == 128) rc = promote ? launch_fwd<128, true, 2>(maps, fp, grid, st) : launch_fwd<128, false, 2>(maps, fp, grid, st);
+    else rc = promote ? launch_fwd<64, true, 2>(maps, fp, grid, st) : launch_fwd<64, false, 2>(maps, fp, grid, st);
+  } else {
+    if (bn == 256) rc = launch_fwd<256, false, 1>(maps, fp, grid, st);
+    else if (bn == 192) rc = launch_fwd<192, false, 1>(maps, fp, grid, st);
+    else if (bn == 128) rc = promote ? launch_fwd<128, true, 1>(maps, fp, grid, st) : launch_fwd<128, false, 1>(maps, fp, grid, st);
+    else rc = promote ? launch_fwd<64, true, 1>(maps, fp, grid, st) : launch_fwd<64, false, 1>(maps, fp, grid, st);
+  }
   prof_end(0, st);
   if (rc) return rc;
   DVD_LAUNCH_CHECK();
@@ -873,7 +1189,7 @@ int tma_fwd_launch(ConvP& p, cudaStream_t st) {
 bool tma_wgrad_eligible(const ConvP& p) {
   if (impl_pref2() != 2) return false;
   const dvd_conv_desc& d = p.d;
-  if (d.Cin < 32 || d.Cout < 64 || p.M < 4096 || d.in_up) return false;
+  if (p.M < 4096 || d.in_up || ((d.Cin < 32 || d.Cout < 64) && p.M < (1 << 18))) return false;
   if ((int64_t)d.N1 * d.N2 > 65535) return false;
   if (p.DHW % 64 != 0 && 64 % p.DHW != 0) return false;
   tma::TileGeom g;
@@ -887,8 +1203,10 @@ int tma_wgrad_launch(ConvP& p, float* dwp, cudaStream_t st) {
   const int N = d.N1 * d.N2;
   WgP wp;
   if (!tile_geom(64, N, d.D, d.H, d.W, &wp.g)) return fail("internal: geometry%s (%s:%d)", "", __FILE__, __LINE__);
-  const bool promote = promote_enabled();        // k = pixels: every CTA runs hundreds of k-blocks
-  const int bn = (d.Cout >= 256 && !promote) ? 256 : (d.Cout >= 128 ? 128 : 64);
+  const int pmode = promote_mode();
+  const int bn = pick_bn(d.Cout, pmode == 1 ? 128 : 256, false);
+  const bool promote = pmode != 0 && bn <= 128;  // k = pixels: every CTA runs hundreds of k-blocks
+  const bool pair = pair_enabled() && d.Cin % 256 == 0 && bn >= 128;
   const int64_t base = (int64_t)ceil_div(d.Cin, BM) * ceil_div(d.Cout, bn) * p.taps;
   int nsplit = 1;
   if (base < 2 * nsm) {
@@ -923,13 +1241,31 @@ int tma_wgrad_launch(ConvP& p, float* dwp, cudaStream_t st) {
   DVD_TRY(make_act_map(&maps[2], y_hi, N, d.D, d.H, d.W, CoutP, wp.g));
   DVD_TRY(make_act_map(&maps[3], y_lo, N, d.D, d.H, d.W, CoutP, wp.g));
   wp.c = p;
+  {
+    // cluster over (ci-blocks, co-blocks): cm shares the dY tile, cn the X tile
+    const int cib = ceil_div(d.Cin, BM), cob = ceil_div(d.Cout, bn);
+    int want_m = 1, want_n = 1;
+    cluster_override(&want_m, &want_n);
+    wp.cm = (want_m >= 2 && cib % 2 == 0 && bn >= 128) ? 2 : 1;
+    wp.cn = (want_n >= 2 && cob % 2 == 0) ? 2 : 1;
+    if (pair) wp.cm = wp.cn = 1;
+  }
   dim3 grid(ceil_div(d.Cin, BM), ceil_div(d.Cout, bn), p.taps * nsplit);
+  prof_tag(pair ? "wgrad M%d Ci%d Co%d t%d bn%d pair ns%d" : "wgrad M%d Ci%d Co%d t%d bn%d ns%d", p.M, d.Cin, d.Cout,
+           p.taps, bn, nsplit);
   prof_begin(1, 2.0 * p.M * (double)d.Cout * d.Cin * p.taps, st);
   int rc;
-  if (bn == 256) rc = launch_wgrad<256, false>(maps, wp, dwp, grid, st);
-  else if (bn == 128) rc = promote ? launch_wgrad<128, true>(maps, wp, dwp, grid, st)
-                                   : launch_wgrad<128, false>(maps, wp, dwp, grid, st);
-  else rc = promote ? launch_wgrad<64, true>(maps, wp, dwp, grid, st) : launch_wgrad<64, false>(maps, wp, dwp, grid, st);
+  if (pair) {
+    if (bn == 256) rc = launch_wgrad<256, false, 2>(maps, wp, dwp, grid, st);
+    else rc = promote ? launch_wgrad<128, true, 2>(maps, wp, dwp, grid, st)
+                      : launch_wgrad<128, false, 2>(maps, wp, dwp, grid, st);
+  } else {
+    if (bn == 256) rc = launch_wgrad<256, false, 1>(maps, wp, dwp, grid, st);
+    else if (bn == 128) rc = promote ? launch_wgrad<128, true, 1>(maps, wp, dwp, grid, st)
+                                     : launch_wgrad<128, false, 1>(maps, wp, dwp, grid, st);
+    else rc = promote ? launch_wgrad<64, true, 1>(maps, wp, dwp, grid, st)
+                      : launch_wgrad<64, false, 1>(maps, wp, dwp, grid, st);
+  }
   prof_end(1, st);
   if (rc) return rc;
   DVD_LAUNCH_CHECK();

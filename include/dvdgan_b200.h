@@ -32,6 +32,9 @@ long long dvd_launch_count(void);
  * returns the summed device time (ms), algorithmic FLOPs and launch count, and resets the category. */
 int dvd_prof_enable(int on);
 int dvd_prof_read(int category, double* ms, double* flops, long long* launches);
+/* per-shape table of the launches recorded so far (not cleared): "category \t tag \t launches \t ms \t flops-or-bytes";
+ * category 2 = operand-plane preparation of the tcgen05 engine (value column = bytes moved) */
+int dvd_prof_dump(const char* path);
 
 /* ------------------------------------------------------------------------------------------
  * Dense engines

