@@ -45,6 +45,7 @@ using namespace dvd;
 extern "C" int dvd_attn_fwd(const float* q, int64_t q_bs, const float* k, int64_t k_bs, const float* v, int64_t v_bs,
                             float* attn, float* out, int64_t o_bs, int batch, int dq, int dv, int Nq, int Nk,
                             int q_token_major, void* stream) {
+  dvd::ProfScope _ps(3, "attn_fwd", dvd::as_stream(stream));
   DVD_CHECK_ARG(q && k && v && attn && out && batch > 0 && dq > 0 && dv > 0 && Nq > 0 && Nk > 0);
   const int64_t a_bs = (int64_t)Nq * Nk;
   for (int b0 = 0; b0 < batch; b0 += 65535) {
@@ -69,6 +70,7 @@ extern "C" int dvd_attn_bwd(const float* q, int64_t q_bs, const float* k, int64_
                             const float* attn, float* dattn, const float* dout, int64_t do_bs, float* dq_,
                             int64_t dq_bs, float* dk_, int64_t dk_bs, float* dv_, int64_t dv_bs, int batch, int dq,
                             int dv, int Nq, int Nk, int q_token_major, void* stream) {
+  dvd::ProfScope _ps(3, "attn_bwd", dvd::as_stream(stream));
   DVD_CHECK_ARG(q && k && v && attn && dattn && dout && dq_ && dk_ && dv_);
   DVD_CHECK_ARG(batch > 0 && dq > 0 && dv > 0 && Nq > 0 && Nk > 0);
   const int64_t a_bs = (int64_t)Nq * Nk;

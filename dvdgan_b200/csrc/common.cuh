@@ -18,6 +18,14 @@ void prof_begin(int category, double flops, cudaStream_t st);
 void prof_end(int category, cudaStream_t st);
 void prof_tag(const char* fmt, int a = 0, int b = 0, int c = 0, int d = 0, int e = 0, int f = 0);   // label of the next record
 
+// RAII bracket for a whole C-ABI call (category 3 = memory-bound helpers): tag = the entry point's name
+struct ProfScope {
+  int cat;
+  cudaStream_t st;
+  ProfScope(int c, const char* tag, cudaStream_t s) : cat(c), st(s) { prof_tag(tag); prof_begin(c, 0.0, s); }
+  ~ProfScope() { prof_end(cat, st); }
+};
+
 inline int fail(const char* fmt, const char* a = "", const char* file = "", int line = 0) {
   snprintf(g_last_error, sizeof(g_last_error), fmt, a, file, line);
   return 1;

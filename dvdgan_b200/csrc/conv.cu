@@ -326,6 +326,27 @@ static int launch_fwd(ConvP& p, cudaStream_t st) {
 
 }  // namespace dvd
 
+namespace dvd {
+// library-internal: forward conv on the TMA/tcgen05 engine with pre-split operands and/or a ConvGRU epilogue
+bool conv_fwd_ex_eligible(const dvd_conv_desc* d) {
+  if (check_desc(d)) return false;
+  ConvP p;
+  fill_common(p, d);
+  return tma_fwd_launch_ex_eligible(p);
+}
+int conv_fwd_ex(const dvd_conv_desc* d, const float* x, const float* w_packed, float* y, const TmaOperands* ops,
+                const GruEpi* epi, cudaStream_t st) {
+  DVD_TRY(check_desc(d));
+  DVD_CHECK_ARG(y && (x || (ops && ops->a_hi)) && (w_packed || (ops && ops->w_hi)));
+  ConvP p;
+  fill_common(p, d);
+  p.x = x; p.w = w_packed; p.bias = nullptr; p.res = nullptr; p.y = y;
+  p.vecB = p.vecY = 0;
+  if (!tma_fwd_launch_ex_eligible(p)) return fail("conv_fwd_ex: shape not eligible%s (%s:%d)", "", __FILE__, __LINE__);
+  return tma_fwd_launch_ex(p, ops, epi, st);
+}
+}  // namespace dvd
+
 using namespace dvd;
 
 extern "C" int dvd_conv_fwd(const dvd_conv_desc* d, const float* x, const float* w_packed, const float* bias,
@@ -600,6 +621,7 @@ __global__ void weight_unpack_kernel(const float* __restrict__ src, int src_ld, 
 extern "C" int dvd_weight_pack(const float* w, int Ci_total, int taps, int co0, int Cout, int ci0, int Cin,
                                const float* sigma, int transpose, float* dst, int dst_rows, int dst_row_off,
                                int dst_ld, int dst_col_off, void* stream) {
+  dvd::ProfScope _ps(3, "weight_pack", dvd::as_stream(stream));
   DVD_CHECK_ARG(w && dst && Ci_total > 0 && taps > 0 && Cout > 0 && Cin > 0 && ci0 >= 0 && co0 >= 0);
   DVD_CHECK_ARG(ci0 + Cin <= Ci_total);
   const int64_t total = (int64_t)taps * Cin * Cout;
@@ -612,6 +634,7 @@ extern "C" int dvd_weight_pack(const float* w, int Ci_total, int taps, int co0, 
 
 extern "C" int dvd_weight_unpack(const float* src, int src_ld, int src_off, int Ci_total, int taps, int co0, int Cout,
                                  int ci0, int Cin, int accumulate, float* w_grad, void* stream) {
+  dvd::ProfScope _ps(3, "weight_unpack", dvd::as_stream(stream));
   DVD_CHECK_ARG(src && w_grad && Ci_total > 0 && taps > 0 && Cout > 0 && Cin > 0);
   DVD_CHECK_ARG(ci0 + Cin <= Ci_total);
   const int64_t total = (int64_t)taps * Cin * Cout;
@@ -700,6 +723,7 @@ __global__ void __launch_bounds__(256) bgemm_kernel(int transA, int transB, int 
 extern "C" int dvd_bgemm(int transA, int transB, int M, int N, int K, float alpha, const float* A, int lda,
                          int64_t strideA, const float* B, int ldb, int64_t strideB, float beta, float* C, int ldc,
                          int64_t strideC, int batch, const float* bias, void* stream) {
+  dvd::ProfScope _ps(3, "bgemm", dvd::as_stream(stream));
   DVD_CHECK_ARG(A && B && C && M > 0 && N > 0 && K >= 0 && batch > 0 && batch <= 65535);
   dim3 grid(ceil_div(N, 64), ceil_div(M, 64), batch);
   DVD_CHECK_ARG(grid.y <= 65535);
@@ -721,11 +745,11 @@ struct ProfRec { cudaEvent_t a, b; double flops; char tag[56]; };
 thread_local char g_prof_tag[56] = "";
 std::mutex g_prof_mu;
 bool g_prof_on = false;
-constexpr int kProfCats = 3;       // 0: conv fwd/dgrad GEMM, 1: wgrad GEMM, 2: operand-plane preparation
+constexpr int kProfCats = 4;       // 0: conv fwd/dgrad GEMM, 1: wgrad GEMM, 2: operand-plane preparation, 3: helpers
 std::vector<ProfRec> g_prof[kProfCats];
 std::vector<ProfRec> g_pool;       // recycled event pairs
-long long g_prof_dropped[kProfCats] = {0, 0, 0};
-constexpr size_t kProfMax = 1 << 16;
+long long g_prof_dropped[kProfCats] = {0, 0, 0, 0};
+constexpr size_t kProfMax = 1 << 17;
 }  // namespace
 
 void prof_begin(int cat, double flops, cudaStream_t st) {

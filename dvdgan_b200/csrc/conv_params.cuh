@@ -23,6 +23,49 @@ int tc_fwd_launch(ConvP& p, cudaStream_t st);
 bool tc_wgrad_eligible(const ConvP& p);
 int tc_wgrad_launch(ConvP& p, float* dwp, cudaStream_t st);
 
+// Optional extras of the TMA + tcgen05 forward engine (library-internal, used by the ConvGRU time loop).
+// Pre-split operand planes: activations [N][D*H*W][CinP] and weights [taps][CoutP][CinP], each as a hi and a lo
+// plane of 16-bit floats (fp16 with lo scaled by 2^11 for forward activations, see conv_tma.cu).
+struct TmaOperands {
+  const void* a_hi = nullptr;     // nullptr: split p.x inside the call
+  const void* a_lo = nullptr;
+  const void* w_hi = nullptr;     // nullptr: split p.w inside the call
+  const void* w_lo = nullptr;
+  int CoutP = 0;                  // rows per tap of the weight planes
+};
+// ConvGRU epilogues (ConvGRU.py:47-52) applied to v = accumulator + y (y holds the x-half pre-activations):
+//  mode 1 (h-half of update|reset, Cout = 2*Ch): co <  Ch: y = u = sigmoid(v)
+//                                                co >= Ch: y = r = sigmoid(v); out2 = r * hprev  (+ planes of it)
+//  mode 2 (h-half of out, Cout = Ch):            y = o = tanh(v); out2 = hprev * (1 - u) + o * u  (+ planes of it)
+// hprev / ugate / out2 are (B, Ch, H, W) views with batch strides hp_s1 / u_s1 / o2_s1 and channel stride H*W;
+// the planes are dense [B*H*W][pl_Cp] fp16 (hi, lo * 2^11), the A operand of the next h-half GEMM.
+struct GruEpi {
+  int mode = 0;
+  int Ch = 0;
+  const float* hprev = nullptr;
+  int64_t hp_s1 = 0;
+  const float* ugate = nullptr;
+  int64_t u_s1 = 0;
+  float* out2 = nullptr;
+  int64_t o2_s1 = 0;
+  void* pl_hi = nullptr;
+  void* pl_lo = nullptr;
+  int pl_Cp = 0;
+};
+bool tma_fwd_launch_ex_eligible(const ConvP& p);
+int tma_fwd_launch_ex(ConvP& p, const TmaOperands* ops, const GruEpi* epi, cudaStream_t st);
+// split fp32 packed weights [taps][Cin][Cout] / activations into planes (fp16 = 1: forward operands)
+int tma_split_weights(const float* w_packed, int taps, int Cin, int Cout, int CoutP, int fp16, void* hi, void* lo,
+                      cudaStream_t st);
+int tma_split_activations(const float* x, int N, int C, int64_t n_stride, int64_t c_stride, int pix, int fp16, void* hi,
+                          void* lo, cudaStream_t st);
+inline int tma_round64(int c) { return (c + 63) / 64 * 64; }
+bool tma_forward_planes_fp16();   // forward operands are split into fp16 planes (default; env DVD_TC_FMT=bf16 turns it off)
+
+bool conv_fwd_ex_eligible(const dvd_conv_desc* d);
+int conv_fwd_ex(const dvd_conv_desc* d, const float* x, const float* w_packed, float* y, const TmaOperands* ops,
+                const GruEpi* epi, cudaStream_t st);
+
 // TMA + tcgen05 path (conv_tma.cu)
 bool tma_fwd_eligible(const ConvP& p);
 int tma_fwd_launch(ConvP& p, cudaStream_t st);

@@ -56,6 +56,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "memory");
   } while (!done);
 }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -429,7 +430,29 @@ struct FwdP {
   float lo_inv;         // 1 / scale of the low-order planes
   int cm, cn;           // CG = 1 only: cluster = cm m-tiles x cn n-tiles, the A tile is multicast to the cn CTAs of an
                         // m-tile (each loads 1/cn of its rows), the B tile to the cm CTAs of an n-tile
+  GruEpi gru;           // ConvGRU gate / state epilogue (mode 0: plain conv epilogue)
 };
+
+// 32 consecutive channels of one pixel -> fp16 hi / lo planes (same split as prep_planes_kernel, fp16 = 1)
+__device__ __forceinline__ void store_planes32(__half* hi, __half* lo, const float* v) {
+  const float lim = 65504.f;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float a = v[q * 8 + 2 * i], b = v[q * 8 + 2 * i + 1];
+      const __half2 hp = __floats2half2_rn(fminf(fmaxf(a, -lim), lim), fminf(fmaxf(b, -lim), lim));
+      const float2 hf = __half22float2(hp);
+      const float ra = (a - hf.x) * kLoScaleFp16, rb = (b - hf.y) * kLoScaleFp16;
+      const __half2 lp = __floats2half2_rn(fminf(fmaxf(ra, -lim), lim), fminf(fmaxf(rb, -lim), lim));
+      h[i] = *reinterpret_cast<const uint32_t*>(&hp);
+      l[i] = *reinterpret_cast<const uint32_t*>(&lp);
+    }
+    reinterpret_cast<uint4*>(hi)[q] = make_uint4(h[0], h[1], h[2], h[3]);
+    reinterpret_cast<uint4*>(lo)[q] = make_uint4(l[0], l[1], l[2], l[3]);
+  }
+}
 
 template <int BN, bool PROMOTE, int CG>
 __global__ void __launch_bounds__(NT, 1)
@@ -574,7 +597,46 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
     // 32 output channels of this thread's pixel.  Everything that has to be READ (previous value for accumulate,
     // residual, bias) is fetched for all 32 channels before the first store: a load-add-store chain per channel
     // would serialise 256 DRAM round trips per tile (measured: +60 % on the per-timestep h-half GEMMs).
+    const GruEpi& ge = fp.gru;
+    // ConvGRU epilogue for 32 channels (Ch % 32 == 0, so a chunk never straddles the update | reset boundary)
+    auto emit_gru32 = [&](int cb, const float* v) {
+      const int co0 = n0 + cb;
+      if (co0 >= d.Cout) return;
+      const int nb = m / p.DHW;                      // image (= batch row) and pixel of this thread
+      const int pix = m - nb * p.DHW;
+      float pre[32], hp[32] = {}, ug[32] = {};
+      const bool state = ge.mode == 2 || co0 >= ge.Ch;        // chunk that produces out2 (r*h or the new h)
+      const int c0 = ge.mode == 2 ? co0 : co0 - ge.Ch;        // channel inside the hidden state
+#pragma unroll
+      for (int j = 0; j < 32; ++j) pre[j] = __ldcg(p.y + yo + (int64_t)(co0 + j) * d.y_cs);
+      if (state) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          hp[j] = ge.hprev ? __ldg(ge.hprev + (int64_t)nb * ge.hp_s1 + (int64_t)(c0 + j) * p.DHW + pix) : 0.f;
+      }
+      if (ge.mode == 2) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) ug[j] = __ldcg(ge.ugate + (int64_t)nb * ge.u_s1 + (int64_t)(c0 + j) * p.DHW + pix);
+      }
+      float o2[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float a = v[j] + pre[j];
+        const float g = ge.mode == 2 ? tanhf(a) : sigmoidf_(a);
+        p.y[yo + (int64_t)(co0 + j) * d.y_cs] = g;
+        if (ge.mode == 2) o2[j] = hp[j] * (1.f - ug[j]) + g * ug[j];
+        else o2[j] = g * hp[j];
+      }
+      if (state) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) ge.out2[(int64_t)nb * ge.o2_s1 + (int64_t)(c0 + j) * p.DHW + pix] = o2[j];
+        if (ge.pl_hi)
+          store_planes32(reinterpret_cast<__half*>(ge.pl_hi) + (int64_t)m * ge.pl_Cp + c0,
+                         reinterpret_cast<__half*>(ge.pl_lo) + (int64_t)m * ge.pl_Cp + c0, o2);
+      }
+    };
     auto emit32 = [&](int cb, const float* v) {
+      if (ge.mode) { emit_gru32(cb, v); return; }
       const int co0 = n0 + cb;
       if (co0 >= d.Cout) return;
       float add[32];
@@ -609,6 +671,22 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
         }
       }
     };
+    // While the main loop runs these warps are idle: pull everything the epilogue will read into L2, so its loads pay
+    // an L2 hit instead of a DRAM round trip per 32-channel chunk.
+    if (ok && !p.atomic_out && (d.accumulate || ge.mode)) {
+      const int nb = m / p.DHW, pix = m - nb * p.DHW;
+      const int cend = min(BN, d.Cout - n0);
+      for (int j = 0; j < cend; ++j) prefetch_l2(p.y + yo + (int64_t)(n0 + j) * d.y_cs);
+      if (ge.mode) {
+        for (int j = 0; j < cend; ++j) {
+          const int co = n0 + j;
+          if (ge.mode == 1 && co < ge.Ch) continue;
+          const int c = ge.mode == 2 ? co : co - ge.Ch;
+          if (ge.hprev) prefetch_l2(ge.hprev + (int64_t)nb * ge.hp_s1 + (int64_t)c * p.DHW + pix);
+          if (ge.mode == 2) prefetch_l2(ge.ugate + (int64_t)nb * ge.u_s1 + (int64_t)c * p.DHW + pix);
+        }
+      }
+    }
     if constexpr (PROMOTE) {
       float acc[BN];
       collect_promoted<BN, C::STAGES, CG>(bars, taddr, n_iters, fp.lo_inv, acc);
@@ -1009,14 +1087,14 @@ static int launch_wgrad(const CUtensorMap* m, const WgP& wp, float* dwp, dim3 gr
 // accumulator policy.  The tensor core truncates its fp32 accumulator on every add (a bias of ~K/16 * 2^-25 relative:
 // 1.4e-5 at K = 12800, measured).  With PROMOTE (BN <= 128, three TMEM regions) the main accumulator is drained into
 // fp32 registers every 8 k-blocks; the 192/256-wide tiles that the SM-ingest roofline wants have no TMEM left for it.
-// env DVD_TC_PROMOTE: unset/"auto" = promote only where the tile is <= 128 wide anyway, "1" = always (caps tiles at
-// 128 columns), "0" = never.  Measured at G's output (ch = 32, 48 frames): 1.3e-4 rel-L2 vs the fp32 reference with
+// env DVD_TC_PROMOTE: unset/"0" = never (default), "auto" = promote where the tile is <= 128 wide anyway, "1" = always
+// (caps tiles at 128 columns).  Measured at G's output (ch = 32, 48 frames): 1.3e-4 rel-L2 vs the fp32 reference with
 // promotion everywhere, 2.3e-4 without, the reference's own fp32-vs-fp64 error being 1.3e-4 (profiles/).
 static int promote_mode() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("DVD_TC_PROMOTE");
-    v = (e && e[0] == '0') ? 0 : ((e && e[0] == '1') ? 1 : 2);
+    v = (!e || e[0] == '0') ? 0 : (e[0] == '1' ? 1 : 2);
   }
   return v;
 }
@@ -1100,7 +1178,23 @@ bool tma_fwd_eligible(const ConvP& p) {
   return tma::tile_geom(128, d.N1 * d.N2, d.D, d.H, d.W, &g) && tma::get_encode() != nullptr;
 }
 
-int tma_fwd_launch(ConvP& p, cudaStream_t st) {
+int tma_fwd_launch(ConvP& p, cudaStream_t st) { return tma_fwd_launch_ex(p, nullptr, nullptr, st); }
+bool tma_fwd_launch_ex_eligible(const ConvP& p) { return tma_fwd_eligible(p); }
+bool tma_forward_planes_fp16() { return tma::lo_fp16_enabled(); }
+
+int tma_split_weights(const float* w_packed, int taps, int Cin, int Cout, int CoutP, int fp16, void* hi, void* lo,
+                      cudaStream_t st) {
+  // [tap][Cin][Cout] fp32 -> [tap][CoutP][CinP]   (image = tap, channel = cin, pixel = cout)
+  return tma::prep_planes(w_packed, taps, 1, Cin, tma_round64(Cin), (int64_t)Cin * Cout, 0, Cout, Cout, CoutP, 1, 1, 0,
+                          0, fp16, reinterpret_cast<__nv_bfloat16*>(hi), reinterpret_cast<__nv_bfloat16*>(lo), st);
+}
+int tma_split_activations(const float* x, int N, int C, int64_t n_stride, int64_t c_stride, int pix, int fp16, void* hi,
+                          void* lo, cudaStream_t st) {
+  return tma::prep_planes(x, N, 1, C, tma_round64(C), n_stride, 0, c_stride, pix, pix, 1, 1, 0, 0, fp16,
+                          reinterpret_cast<__nv_bfloat16*>(hi), reinterpret_cast<__nv_bfloat16*>(lo), st);
+}
+
+int tma_fwd_launch_ex(ConvP& p, const TmaOperands* ops, const GruEpi* epi, cudaStream_t st) {
   using namespace tma;
   const dvd_conv_desc& d = p.d;
   const int nsm = num_sms();
@@ -1115,13 +1209,16 @@ int tma_fwd_launch(ConvP& p, cudaStream_t st) {
   const int mt = ceil_div(p.M, BM);
   if (bn > 128 && (int64_t)mt * ceil_div(d.Cout, bn) < nsm) bn = 128;        // small grids: more, narrower tiles
   const bool promote = pmode != 0 && bn <= 128 && p.iters_total > PROMOTE_MIN;
-  const int CoutP = round_up(d.Cout, bn);
+  const bool ext_w = ops && ops->w_hi, ext_a = ops && ops->a_hi;
+  const int CoutP = ext_w ? ops->CoutP : round_up(d.Cout, bn);
   fp.CoutP = CoutP;
+  if (epi) fp.gru = *epi;
+  if (fp.gru.mode) DVD_CHECK_ARG(d.accumulate && fp.gru.Ch % 32 == 0 && !d.out_act && !p.res && !p.bias);
   fp.fp16 = (lo_fp16_enabled() && d.x_kind == 1) ? 1 : 0;
   fp.lo_inv = fp.fp16 ? 1.f / kLoScaleFp16 : 1.f / kLoScaleBf16;
   const int64_t ctas = (int64_t)mt * ceil_div(d.Cout, bn);
   int nsplit = 1;
-  if (ctas < nsm && d.out_act == 0 && p.iters_total >= 8) {
+  if (ctas < nsm && d.out_act == 0 && p.iters_total >= 8 && !fp.gru.mode) {
     nsplit = (int)ceil_div<int64_t>(nsm, ctas);
     const int maxs = p.iters_total / 4;
     if (nsplit > maxs) nsplit = maxs;
@@ -1140,16 +1237,29 @@ int tma_fwd_launch(ConvP& p, cudaStream_t st) {
   const size_t a_elems = (size_t)N * pix * CinP;
   const size_t w_elems = (size_t)p.taps * CoutP * CinP;
   Scratch sc;
-  DVD_TRY(sc.alloc((2 * a_elems + 2 * w_elems) * sizeof(__nv_bfloat16) + 1024, st));
-  __nv_bfloat16* a_hi = reinterpret_cast<__nv_bfloat16*>(sc.ptr);
-  __nv_bfloat16* a_lo = a_hi + a_elems;
-  __nv_bfloat16* w_hi = a_lo + a_elems;
-  __nv_bfloat16* w_lo = w_hi + w_elems;
-  DVD_TRY(prep_planes(p.x, d.N1, d.N2, d.Cin, CinP, d.x_s1, d.x_s2, d.x_cs, p.DHW, p.DHW, d.W, p.HW, d.in_up,
-                      d.in_relu, fp.fp16, a_hi, a_lo, st));
-  // weights: [tap][Cin][Cout] fp32 -> [tap][CoutP][CinP]   (image = tap, channel = cin, pixel = cout)
-  DVD_TRY(prep_planes(p.w, p.taps, 1, d.Cin, CinP, (int64_t)d.Cin * d.Cout, 0, d.Cout, d.Cout, CoutP, 1, 1, 0, 0,
-                      fp.fp16, w_hi, w_lo, st));
+  const size_t need = (ext_a ? 0 : 2 * a_elems) + (ext_w ? 0 : 2 * w_elems);
+  if (need) DVD_TRY(sc.alloc(need * sizeof(__nv_bfloat16) + 1024, st));
+  __nv_bfloat16* cur = reinterpret_cast<__nv_bfloat16*>(sc.ptr);
+  const __nv_bfloat16 *a_hi, *a_lo, *w_hi, *w_lo;
+  if (ext_a) {
+    a_hi = reinterpret_cast<const __nv_bfloat16*>(ops->a_hi);
+    a_lo = reinterpret_cast<const __nv_bfloat16*>(ops->a_lo);
+  } else {
+    __nv_bfloat16* h = cur; __nv_bfloat16* l = cur + a_elems; cur += 2 * a_elems;
+    DVD_TRY(prep_planes(p.x, d.N1, d.N2, d.Cin, CinP, d.x_s1, d.x_s2, d.x_cs, p.DHW, p.DHW, d.W, p.HW, d.in_up,
+                        d.in_relu, fp.fp16, h, l, st));
+    a_hi = h; a_lo = l;
+  }
+  if (ext_w) {
+    w_hi = reinterpret_cast<const __nv_bfloat16*>(ops->w_hi);
+    w_lo = reinterpret_cast<const __nv_bfloat16*>(ops->w_lo);
+  } else {
+    __nv_bfloat16* h = cur; __nv_bfloat16* l = cur + w_elems;
+    // weights: [tap][Cin][Cout] fp32 -> [tap][CoutP][CinP]   (image = tap, channel = cin, pixel = cout)
+    DVD_TRY(prep_planes(p.w, p.taps, 1, d.Cin, CinP, (int64_t)d.Cin * d.Cout, 0, d.Cout, d.Cout, CoutP, 1, 1, 0, 0,
+                        fp.fp16, h, l, st));
+    w_hi = h; w_lo = l;
+  }
   CUtensorMap maps[4];
   // CTA pairs (256 x bn tiles) whenever there is more than one wave of tiles; otherwise optional multicast clusters,
   // only where the slices are still legal TMA boxes

@@ -5,7 +5,10 @@
 // (B,T,3Ch,H,W) buffer = (update, reset, out) that is activated in place and, in the backward sweep,
 // overwritten in place with the pre-activation gradients, which then feed ONE batched x-dgrad and the batched
 // weight gradients.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
+#include "conv_params.cuh"
 
 namespace dvd {
 
@@ -89,6 +92,10 @@ struct GruWs {
   float *dwx, *dwhur, *dwho;            // packed weight grads
   float *d_rh, *carry0, *carry1, *dbias;
   double* dscratch;
+  // fused forward path: fp16 hi/lo planes of the h-half weights and of the per-step GEMM inputs
+  uint16_t *whur_hi, *whur_lo, *who_hi, *who_lo;      // [taps][CoutP][ChP]
+  uint16_t *hpl_hi[2], *hpl_lo[2];                    // planes of h_{t-1} / h_t (ping-pong), [B*HW][ChP]
+  uint16_t *rhpl_hi, *rhpl_lo;                        // planes of r * h_{t-1}
   size_t bytes;
 };
 
@@ -113,8 +120,27 @@ static GruWs carve(void* base, int B, int Cx, int Ch, int HW, int taps, bool bwd
     w.wxT = w.whurT = w.whoT = w.dwx = w.dwhur = w.dwho = w.d_rh = w.carry0 = w.carry1 = w.dbias = nullptr;
     w.dscratch = nullptr;
   }
+  {
+    const size_t ChP = (size_t)tma_round64(Ch), Co2P = (size_t)tma_round64(2 * Ch);
+    auto take16 = [&](size_t n) { return reinterpret_cast<uint16_t*>(take((n + 1) / 2)); };
+    w.whur_hi = take16((size_t)taps * Co2P * ChP); w.whur_lo = take16((size_t)taps * Co2P * ChP);
+    w.who_hi = take16((size_t)taps * ChP * ChP); w.who_lo = take16((size_t)taps * ChP * ChP);
+    const size_t pl = (size_t)B * HW * ChP;
+    for (int i = 0; i < 2; ++i) { w.hpl_hi[i] = take16(pl); w.hpl_lo[i] = take16(pl); }
+    w.rhpl_hi = take16(pl); w.rhpl_lo = take16(pl);
+  }
   w.bytes = off;
   return w;
+}
+
+// env DVD_GRU_FUSED=0: keep the gate math in separate elementwise kernels
+static bool gru_fused_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DVD_GRU_FUSED");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
 }
 
 static dvd_conv_desc base_desc(int B, int T, int Cin, int Cout, int H, int W, int k) {
@@ -161,24 +187,65 @@ extern "C" int dvd_convgru_layer_fwd(const float* x, int64_t x_bs, int64_t x_ts,
     DVD_TRY(dvd_conv_fwd(&d, x, ws.wx, ws.bias, nullptr, gates, stream));
   }
   const int eb = ew_blocks((int64_t)B * chw);
+  // Fused path: the two h-half GEMMs of a step run on the TMA/tcgen05 engine with the gate math in their epilogues
+  // (update|reset: sigmoid, r*h;  out: tanh, state update) which also emit the fp16 planes the next GEMM reads, and the
+  // h-half weight planes are split once per layer instead of once per step.
+  dvd_conv_desc d_ur = base_desc(B, 1, Ch, 2 * Ch, H, W, k), d_o = base_desc(B, 1, Ch, Ch, H, W, k);
+  d_ur.x_kind = d_o.x_kind = 1; d_ur.accumulate = d_o.accumulate = 1;
+  d_ur.y_s1 = d_o.y_s1 = g_bs; d_ur.x_s1 = d_o.x_s1 = chw;
+  const int ChP = tma_round64(Ch), Co2P = tma_round64(2 * Ch);
+  const bool fused = gru_fused_enabled() && T > 1 && Ch % 32 == 0 && tma_forward_planes_fp16() &&
+                     conv_fwd_ex_eligible(&d_ur) && conv_fwd_ex_eligible(&d_o);
+  if (fused) {
+    DVD_TRY(tma_split_weights(ws.whur, taps, Ch, 2 * Ch, Co2P, 1, ws.whur_hi, ws.whur_lo, st));
+    DVD_TRY(tma_split_weights(ws.who, taps, Ch, Ch, ChP, 1, ws.who_hi, ws.who_lo, st));
+    if (ChP != Ch) {      // padded channels of the planes the epilogues write stay zero
+      const size_t pl = (size_t)B * HW * ChP * sizeof(uint16_t);
+      for (int i = 0; i < 2; ++i) {
+        DVD_CUDA(cudaMemsetAsync(ws.hpl_hi[i], 0, pl, st));
+        DVD_CUDA(cudaMemsetAsync(ws.hpl_lo[i], 0, pl, st));
+      }
+      DVD_CUDA(cudaMemsetAsync(ws.rhpl_hi, 0, pl, st));
+      DVD_CUDA(cudaMemsetAsync(ws.rhpl_lo, 0, pl, st));
+    }
+  }
+  bool have_planes = false;       // planes of h_{t-1} already sit in slot (t-1) & 1
   for (int t = 0; t < T; ++t) {
     const float* hp = t > 0 ? h + (int64_t)(t - 1) * h_ts : h0;
     const int64_t hp_bs = t > 0 ? h_bs : chw;
     float* g_t = gates + (int64_t)t * g_ts;
     float* rh_t = rh + (int64_t)t * h_ts;
+    if (fused && hp) {
+      const int sp = (t + 1) & 1, sn = t & 1;          // slots of h_{t-1} and h_t
+      if (!have_planes)
+        DVD_TRY(tma_split_activations(hp, B, Ch, hp_bs, HW, HW, 1, ws.hpl_hi[sp], ws.hpl_lo[sp], st));
+      TmaOperands op;
+      GruEpi ge;
+      op.a_hi = ws.hpl_hi[sp]; op.a_lo = ws.hpl_lo[sp]; op.w_hi = ws.whur_hi; op.w_lo = ws.whur_lo; op.CoutP = Co2P;
+      ge.mode = 1; ge.Ch = Ch; ge.hprev = hp; ge.hp_s1 = hp_bs; ge.out2 = rh_t; ge.o2_s1 = h_bs;
+      ge.pl_hi = ws.rhpl_hi; ge.pl_lo = ws.rhpl_lo; ge.pl_Cp = ChP;
+      DVD_TRY(conv_fwd_ex(&d_ur, nullptr, nullptr, g_t, &op, &ge, st));
+      op.a_hi = ws.rhpl_hi; op.a_lo = ws.rhpl_lo; op.w_hi = ws.who_hi; op.w_lo = ws.who_lo; op.CoutP = ChP;
+      ge.mode = 2; ge.ugate = g_t; ge.u_s1 = g_bs; ge.out2 = h + (int64_t)t * h_ts; ge.o2_s1 = h_bs;
+      ge.pl_hi = ws.hpl_hi[sn]; ge.pl_lo = ws.hpl_lo[sn];
+      DVD_TRY(conv_fwd_ex(&d_o, nullptr, nullptr, g_t + 2 * chw, &op, &ge, st));
+      have_planes = true;
+      continue;
+    }
+    have_planes = false;
     if (hp) {
       dvd_conv_desc d = base_desc(B, 1, Ch, 2 * Ch, H, W, k); d.x_kind = 1;
       d.x_s1 = hp_bs; d.y_s1 = g_bs; d.accumulate = 1;
       DVD_TRY(dvd_conv_fwd(&d, hp, ws.whur, nullptr, nullptr, g_t, stream));
     }
-    gru_gate_ur_kernel<<<eb, 256, 0, st>>>(g_t, g_bs, hp, hp_bs, rh_t, h_bs, B, chw);
+    { ProfScope ps(3, "gru_gate_ur", st); gru_gate_ur_kernel<<<eb, 256, 0, st>>>(g_t, g_bs, hp, hp_bs, rh_t, h_bs, B, chw); }
     DVD_LAUNCH_CHECK();
     if (hp) {
       dvd_conv_desc d = base_desc(B, 1, Ch, Ch, H, W, k); d.x_kind = 1;
       d.x_s1 = h_bs; d.y_s1 = g_bs; d.accumulate = 1;
       DVD_TRY(dvd_conv_fwd(&d, rh_t, ws.who, nullptr, nullptr, g_t + 2 * chw, stream));
     }
-    gru_out_kernel<<<eb, 256, 0, st>>>(g_t, g_bs, hp, hp_bs, h + (int64_t)t * h_ts, h_bs, B, chw);
+    { ProfScope ps(3, "gru_out", st); gru_out_kernel<<<eb, 256, 0, st>>>(g_t, g_bs, hp, hp_bs, h + (int64_t)t * h_ts, h_bs, B, chw); }
     DVD_LAUNCH_CHECK();
   }
   return 0;
@@ -214,14 +281,14 @@ extern "C" int dvd_convgru_layer_bwd(const float* x, int64_t x_bs, int64_t x_ts,
     const float* hp = t > 0 ? h + (int64_t)(t - 1) * h_ts : h0;
     const int64_t hp_bs = t > 0 ? h_bs : chw;
     float* g_t = gates + (int64_t)t * g_ts;
-    gru_bwd1_kernel<<<eb, 256, 0, st>>>(g_t, g_bs, hp, hp_bs, dh + (int64_t)t * h_ts, h_bs, carry_in, carry_out, B, chw);
+    { ProfScope ps(3, "gru_bwd1", st); gru_bwd1_kernel<<<eb, 256, 0, st>>>(g_t, g_bs, hp, hp_bs, dh + (int64_t)t * h_ts, h_bs, carry_in, carry_out, B, chw); }
     DVD_LAUNCH_CHECK();
     if (hp) {
       dvd_conv_desc d = base_desc(B, 1, Ch, Ch, H, W, k);     // d(rh) = conv_o^T(da_o), h-half
       d.x_s1 = g_bs; d.y_s1 = chw;
       DVD_TRY(dvd_conv_fwd(&d, g_t + 2 * chw, ws.whoT, nullptr, nullptr, ws.d_rh, stream));
     }
-    gru_bwd2_kernel<<<eb, 256, 0, st>>>(g_t, g_bs, hp, hp_bs, ws.d_rh, carry_out, B, chw);
+    { ProfScope ps(3, "gru_bwd2", st); gru_bwd2_kernel<<<eb, 256, 0, st>>>(g_t, g_bs, hp, hp_bs, ws.d_rh, carry_out, B, chw); }
     DVD_LAUNCH_CHECK();
     if (hp) {
       dvd_conv_desc d = base_desc(B, 1, 2 * Ch, Ch, H, W, k);  // dh_prev += conv_u^T(da_u) + conv_r^T(da_r)

@@ -50,6 +50,55 @@ __global__ void avgpool_bwd_kernel(const float* __restrict__ dy, int64_t NC, int
   }
 }
 
+// 2x2 spatial pooling (pd = 1) with W a multiple of 4 and W/4 a power of two: rows of the flattened (NC*D*H, W) input
+// map to output row = input row / 2; one thread = two outputs (fwd) / a 2x4 input patch (bwd); 128-bit accesses.
+__global__ void avgpool2x2_fwd_vec_kernel(const float* __restrict__ x, int64_t rows_out, int W, int wq_shift,
+                                          float inv, int accumulate, float* __restrict__ y) {
+  const int Wo = W >> 1;
+  const int64_t total = rows_out << wq_shift;            // (W / 4) vectors per output row
+  GRID_STRIDE(i, total) {
+    const int64_t ro = i >> wq_shift;
+    const int q = (int)(i - (ro << wq_shift));
+    const float4 a = __ldg(reinterpret_cast<const float4*>(x + (2 * ro) * W) + q);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(x + (2 * ro + 1) * W) + q);
+    float2 o = make_float2(((a.x + a.y) + (b.x + b.y)) * inv, ((a.z + a.w) + (b.z + b.w)) * inv);
+    float2* dst = reinterpret_cast<float2*>(y + ro * Wo) + q;
+    if (accumulate) { const float2 p = *dst; o.x += p.x; o.y += p.y; }
+    *dst = o;
+  }
+}
+__global__ void avgpool2x2_bwd_vec_kernel(const float* __restrict__ dy, int64_t rows_out, int W, int wq_shift,
+                                          int accumulate, float* __restrict__ dx) {
+  const int Wo = W >> 1;
+  const int64_t total = rows_out << wq_shift;
+  GRID_STRIDE(i, total) {
+    const int64_t ro = i >> wq_shift;
+    const int q = (int)(i - (ro << wq_shift));
+    const float2 g = __ldg(reinterpret_cast<const float2*>(dy + ro * Wo) + q);
+    float4 o = make_float4(g.x * 0.25f, g.x * 0.25f, g.y * 0.25f, g.y * 0.25f);
+    float4* d0 = reinterpret_cast<float4*>(dx + (2 * ro) * W) + q;
+    float4* d1 = reinterpret_cast<float4*>(dx + (2 * ro + 1) * W) + q;
+    if (accumulate) {
+      const float4 p0 = *d0, p1 = *d1;
+      *d0 = make_float4(p0.x + o.x, p0.y + o.y, p0.z + o.z, p0.w + o.w);
+      *d1 = make_float4(p1.x + o.x, p1.y + o.y, p1.z + o.z, p1.w + o.w);
+    } else {
+      *d0 = o;
+      *d1 = o;
+    }
+  }
+}
+static int pool2x2_shift(const void* a, const void* b, int D, int H, int W, int pd, int ph, int pw) {
+  if (pd != 1 || ph != 2 || pw != 2 || (W & 3) || (H & 1)) return -1;
+  if ((reinterpret_cast<uintptr_t>(a) & 15) || (reinterpret_cast<uintptr_t>(b) & 15)) return -1;
+  const int wq = W >> 2;
+  if (wq & (wq - 1)) return -1;
+  int sh = 0;
+  while ((1 << sh) < wq) ++sh;
+  (void)D;
+  return sh;
+}
+
 __global__ void maxpool_fwd_kernel(const float* __restrict__ x, int64_t NC, int D, int H, int W, int pd, int ph, int pw,
                                    float* __restrict__ y) {
   const int Do = D / pd, Ho = H / ph, Wo = W / pw;
@@ -230,6 +279,8 @@ __global__ void double_to_float_kernel(const double* __restrict__ a, int n, int 
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = accumulate ? out[i] + (float)a[i] : (float)a[i];
 }
+// one (channel, image range) per block: rows of P contiguous floats, 128-bit loads when P % 4 == 0, no per-element
+// division; per-thread fp32 partials over one row, fp64 across rows and blocks
 __global__ void channel_sum_kernel(const float* __restrict__ x, int N, int C, int64_t P, int64_t n_stride,
                                    int n_per_block, double* __restrict__ acc) {
   __shared__ double red[32];
@@ -238,11 +289,33 @@ __global__ void channel_sum_kernel(const float* __restrict__ x, int N, int C, in
   int ne = nb + n_per_block;
   if (ne > N) ne = N;
   double s = 0.0;
-  const int64_t cnt = (int64_t)(ne - nb) * P;
-  for (int64_t i = threadIdx.x; i < cnt; i += blockDim.x) {
-    const int n = nb + (int)(i / P);
-    const int64_t p = i % P;
-    s += __ldg(x + (int64_t)n * n_stride + (int64_t)c * P + p);
+  const bool vec = (P % 4 == 0) && (n_stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+  if (P >= blockDim.x) {
+    for (int n = nb; n < ne; ++n) {
+      const float* row = x + (int64_t)n * n_stride + (int64_t)c * P;
+      float part = 0.f;
+      if (vec) {
+        const float4* r4 = reinterpret_cast<const float4*>(row);
+        const int64_t P4 = P >> 2;
+        for (int64_t i = threadIdx.x; i < P4; i += blockDim.x) {
+          const float4 v = __ldg(r4 + i);
+          part += (v.x + v.y) + (v.z + v.w);
+        }
+      } else {
+        for (int64_t i = threadIdx.x; i < P; i += blockDim.x) part += __ldg(row + i);
+      }
+      s += (double)part;
+    }
+  } else {
+    // short rows (P < blockDim): lay the threads out as (rows per pass) x P
+    const int Pi = (int)P;
+    const int rpp = blockDim.x / Pi;
+    const int r = threadIdx.x / Pi, pp = threadIdx.x - r * Pi;
+    if (r < rpp) {
+      float part = 0.f;
+      for (int n = nb + r; n < ne; n += rpp) part += __ldg(x + (int64_t)n * n_stride + (int64_t)c * P + pp);
+      s = (double)part;
+    }
   }
   s = block_sum(s, red);
   if (threadIdx.x == 0) atomicAdd(acc + c, s);
@@ -355,23 +428,39 @@ using namespace dvd;
 
 extern "C" int dvd_avgpool_fwd(const float* x, int64_t NC, int D, int H, int W, int pd, int ph, int pw, float scale,
                                int accumulate, float* y, void* stream) {
+  dvd::ProfScope _ps(3, "avgpool_fwd", dvd::as_stream(stream));
   DVD_CHECK_ARG(x && y && POOL_ARGS_OK);
   const int64_t total = NC * (D / pd) * (H / ph) * (W / pw);
   DVD_CHECK_ARG(total > 0);
-  avgpool_fwd_kernel<<<ew_blocks(total, 2), 256, 0, as_stream(stream)>>>(x, NC, D, H, W, pd, ph, pw, scale, accumulate, y);
+  const int sh = pool2x2_shift(x, y, D, H, W, pd, ph, pw);
+  if (sh >= 0) {
+    const int64_t rows_out = NC * D * (H / 2);
+    avgpool2x2_fwd_vec_kernel<<<ew_blocks(rows_out << sh, 2), 256, 0, as_stream(stream)>>>(x, rows_out, W, sh, scale * 0.25f,
+                                                                                          accumulate, y);
+  } else {
+    avgpool_fwd_kernel<<<ew_blocks(total, 2), 256, 0, as_stream(stream)>>>(x, NC, D, H, W, pd, ph, pw, scale, accumulate, y);
+  }
   DVD_LAUNCH_CHECK();
   return 0;
 }
 extern "C" int dvd_avgpool_bwd(const float* dy, int64_t NC, int D, int H, int W, int pd, int ph, int pw,
                                int accumulate, float* dx, void* stream) {
+  dvd::ProfScope _ps(3, "avgpool_bwd", dvd::as_stream(stream));
   DVD_CHECK_ARG(dy && dx && POOL_ARGS_OK);
-  avgpool_bwd_kernel<<<ew_blocks(NC * D * H * W, 4), 256, 0, as_stream(stream)>>>(dy, NC, D, H, W, pd, ph, pw,
-                                                                                  accumulate, dx);
+  const int sh = pool2x2_shift(dy, dx, D, H, W, pd, ph, pw);
+  if (sh >= 0) {
+    const int64_t rows_out = NC * D * (H / 2);
+    avgpool2x2_bwd_vec_kernel<<<ew_blocks(rows_out << sh, 2), 256, 0, as_stream(stream)>>>(dy, rows_out, W, sh, accumulate, dx);
+  } else {
+    avgpool_bwd_kernel<<<ew_blocks(NC * D * H * W, 4), 256, 0, as_stream(stream)>>>(dy, NC, D, H, W, pd, ph, pw,
+                                                                                    accumulate, dx);
+  }
   DVD_LAUNCH_CHECK();
   return 0;
 }
 extern "C" int dvd_maxpool_fwd(const float* x, int64_t NC, int D, int H, int W, int pd, int ph, int pw, float* y,
                                void* stream) {
+  dvd::ProfScope _ps(3, "maxpool_fwd", dvd::as_stream(stream));
   DVD_CHECK_ARG(x && y && POOL_ARGS_OK);
   DVD_CHECK_ARG(D % pd == 0 && H % ph == 0 && W % pw == 0);
   const int64_t total = NC * (D / pd) * (H / ph) * (W / pw);
@@ -381,6 +470,7 @@ extern "C" int dvd_maxpool_fwd(const float* x, int64_t NC, int D, int H, int W, 
 }
 extern "C" int dvd_maxpool_bwd(const float* x, const float* dy, int64_t NC, int D, int H, int W, int pd, int ph, int pw,
                                float* dx, void* stream) {
+  dvd::ProfScope _ps(3, "maxpool_bwd", dvd::as_stream(stream));
   DVD_CHECK_ARG(x && dy && dx && POOL_ARGS_OK);
   DVD_CHECK_ARG(D % pd == 0 && H % ph == 0 && W % pw == 0);
   const int64_t total = NC * (D / pd) * (H / ph) * (W / pw);
@@ -389,6 +479,7 @@ extern "C" int dvd_maxpool_bwd(const float* x, const float* dy, int64_t NC, int 
   return 0;
 }
 extern "C" int dvd_phi_fwd(const float* x, int B, int T, int C, int H, int W, float* y, void* stream) {
+  dvd::ProfScope _ps(3, "phi_fwd", dvd::as_stream(stream));
   DVD_CHECK_ARG(x && y && B > 0 && T > 0 && C > 0 && H > 1 && W > 1);
   const int64_t total = (int64_t)B * C * T * (H / 2) * (W / 2);
   phi_fwd_kernel<<<ew_blocks(total, 2), 256, 0, as_stream(stream)>>>(x, B, T, C, H, W, y);
@@ -397,6 +488,7 @@ extern "C" int dvd_phi_fwd(const float* x, int B, int T, int C, int H, int W, fl
 }
 extern "C" int dvd_phi_bwd(const float* dy, int B, int T, int C, int H, int W, int accumulate, float* dx,
                            void* stream) {
+  dvd::ProfScope _ps(3, "phi_bwd", dvd::as_stream(stream));
   DVD_CHECK_ARG(dy && dx && B > 0 && T > 0 && C > 0 && H > 1 && W > 1);
   phi_bwd_kernel<<<ew_blocks((int64_t)B * T * C * H * W, 4), 256, 0, as_stream(stream)>>>(dy, B, T, C, H, W, accumulate,
                                                                                           dx);
@@ -405,6 +497,7 @@ extern "C" int dvd_phi_bwd(const float* dy, int B, int T, int C, int H, int W, i
 }
 extern "C" int dvd_gather_frames_fwd(const float* x, const int64_t* idx, int B, int T, int k, int64_t frame_elems,
                                      float* y, void* stream) {
+  dvd::ProfScope _ps(3, "gather_frames_fwd", dvd::as_stream(stream));
   DVD_CHECK_ARG(x && idx && y && B > 0 && T > 0 && k > 0 && frame_elems > 0);
   gather_frames_kernel<<<ew_blocks((int64_t)B * k * frame_elems, 4), 256, 0, as_stream(stream)>>>(x, idx, B, T, k,
                                                                                                   frame_elems, y);
@@ -413,6 +506,7 @@ extern "C" int dvd_gather_frames_fwd(const float* x, const int64_t* idx, int B, 
 }
 extern "C" int dvd_gather_frames_bwd(const float* dy, const int64_t* idx, int B, int T, int k, int64_t frame_elems,
                                      int accumulate, float* dx, void* stream) {
+  dvd::ProfScope _ps(3, "gather_frames_bwd", dvd::as_stream(stream));
   DVD_CHECK_ARG(dy && idx && dx && B > 0 && T > 0 && k > 0 && frame_elems > 0);
   cudaStream_t st = as_stream(stream);
   if (!accumulate) DVD_CUDA(cudaMemsetAsync(dx, 0, sizeof(float) * (size_t)B * T * frame_elems, st));
@@ -421,12 +515,14 @@ extern "C" int dvd_gather_frames_bwd(const float* dy, const int64_t* idx, int B,
   return 0;
 }
 extern "C" int dvd_permute_bctp(const float* x, int B, int C, int T, int64_t P, float* y, void* stream) {
+  dvd::ProfScope _ps(3, "permute_bctp", dvd::as_stream(stream));
   DVD_CHECK_ARG(x && y && B > 0 && C > 0 && T > 0 && P > 0);
   permute_bctp_kernel<<<ew_blocks((int64_t)B * C * T * P, 4), 256, 0, as_stream(stream)>>>(x, B, C, T, P, y);
   DVD_LAUNCH_CHECK();
   return 0;
 }
 extern "C" int dvd_permute5(const float* x, const int* dims, const int* perm, float* y, void* stream) {
+  dvd::ProfScope _ps(3, "permute5", dvd::as_stream(stream));
   DVD_CHECK_ARG(x && dims && perm && y);
   int64_t str[5];
   int64_t total = 1;
@@ -445,12 +541,14 @@ extern "C" int dvd_permute5(const float* x, const int* dims, const int* perm, fl
   return 0;
 }
 extern "C" int dvd_act_fwd(const float* x, int64_t n, int act, float* y, void* stream) {
+  dvd::ProfScope _ps(3, "act_fwd", dvd::as_stream(stream));
   DVD_CHECK_ARG(x && y && n > 0);
   act_fwd_kernel<<<ew_blocks(n), 256, 0, as_stream(stream)>>>(x, n, act, y);
   DVD_LAUNCH_CHECK();
   return 0;
 }
 extern "C" int dvd_act_bwd(const float* ref, const float* dy, int64_t n, int act, float* dx, void* stream) {
+  dvd::ProfScope _ps(3, "act_bwd", dvd::as_stream(stream));
   DVD_CHECK_ARG(ref && dy && dx && n > 0);
   act_bwd_kernel<<<ew_blocks(n), 256, 0, as_stream(stream)>>>(ref, dy, n, act, dx);
   DVD_LAUNCH_CHECK();
@@ -458,6 +556,7 @@ extern "C" int dvd_act_bwd(const float* ref, const float* dy, int64_t n, int act
 }
 extern "C" int dvd_scale_residual_fwd(const float* o, const float* x, const float* gamma, int64_t n, float* y,
                                       void* stream) {
+  dvd::ProfScope _ps(3, "scale_residual_fwd", dvd::as_stream(stream));
   DVD_CHECK_ARG(o && x && gamma && y && n > 0);
   scale_residual_fwd_kernel<<<ew_blocks(n), 256, 0, as_stream(stream)>>>(o, x, gamma, n, y);
   DVD_LAUNCH_CHECK();
@@ -465,6 +564,7 @@ extern "C" int dvd_scale_residual_fwd(const float* o, const float* x, const floa
 }
 extern "C" int dvd_scale_residual_bwd(const float* o, const float* dy, const float* gamma, int64_t n, float* do_,
                                       float* dgamma, void* scratch, void* stream) {
+  dvd::ProfScope _ps(3, "scale_residual_bwd", dvd::as_stream(stream));
   DVD_CHECK_ARG(o && dy && gamma && do_ && dgamma && scratch && n > 0);
   cudaStream_t st = as_stream(stream);
   double* acc = reinterpret_cast<double*>(scratch);
@@ -477,6 +577,7 @@ extern "C" int dvd_scale_residual_bwd(const float* o, const float* dy, const flo
 }
 extern "C" int dvd_channel_sum(const float* x, int N, int C, int64_t P, int64_t n_stride, int accumulate, float* out,
                                void* scratch, void* stream) {
+  dvd::ProfScope _ps(3, "channel_sum", dvd::as_stream(stream));
   DVD_CHECK_ARG(x && out && scratch && N > 0 && C > 0 && P > 0);
   cudaStream_t st = as_stream(stream);
   double* acc = reinterpret_cast<double*>(scratch);
@@ -493,18 +594,21 @@ extern "C" int dvd_channel_sum(const float* x, int N, int C, int64_t P, int64_t 
   return 0;
 }
 extern "C" int dvd_axpby(const float* x, float a, float b, int64_t n, float* y, void* stream) {
+  dvd::ProfScope _ps(3, "axpby", dvd::as_stream(stream));
   DVD_CHECK_ARG(x && y && n > 0);
   axpby_kernel<<<ew_blocks(n), 256, 0, as_stream(stream)>>>(x, a, b, n, y);
   DVD_LAUNCH_CHECK();
   return 0;
 }
 extern "C" int dvd_embedding_fwd(const float* w, const int64_t* idx, int n, int dim, float* y, void* stream) {
+  dvd::ProfScope _ps(3, "embedding_fwd", dvd::as_stream(stream));
   DVD_CHECK_ARG(w && idx && y && n > 0 && dim > 0);
   embedding_fwd_kernel<<<ew_blocks((int64_t)n * dim, 1), 256, 0, as_stream(stream)>>>(w, idx, n, dim, y);
   DVD_LAUNCH_CHECK();
   return 0;
 }
 extern "C" int dvd_embedding_bwd(const float* dy, const int64_t* idx, int n, int dim, float* dw, void* stream) {
+  dvd::ProfScope _ps(3, "embedding_bwd", dvd::as_stream(stream));
   DVD_CHECK_ARG(dy && idx && dw && n > 0 && dim > 0);
   embedding_bwd_kernel<<<ew_blocks((int64_t)n * dim, 1), 256, 0, as_stream(stream)>>>(dy, idx, n, dim, dw);
   DVD_LAUNCH_CHECK();
@@ -513,6 +617,7 @@ extern "C" int dvd_embedding_bwd(const float* dy, const int64_t* idx, int n, int
 extern "C" int dvd_dhead_fwd(const float* x, int N, int C, int HW, int T, const float* w_lin, const float* sigma_l,
                              const float* b_lin, const float* emb, const float* sigma_e, const int64_t* class_id,
                              float* feat, float* out, void* stream) {
+  dvd::ProfScope _ps(3, "dhead_fwd", dvd::as_stream(stream));
   DVD_CHECK_ARG(x && w_lin && sigma_l && b_lin && emb && sigma_e && class_id && feat && out);
   DVD_CHECK_ARG(N > 0 && C > 0 && HW > 0 && T > 0);
   dhead_fwd_kernel<<<N, 256, 0, as_stream(stream)>>>(x, C, HW, T, w_lin, sigma_l, b_lin, emb, sigma_e, class_id, feat,
@@ -524,6 +629,7 @@ extern "C" int dvd_dhead_bwd(const float* x, const float* feat, const float* dou
                              int n_class, const float* w_lin, const float* sigma_l, const float* emb,
                              const float* sigma_e, const int64_t* class_id, float* dx, float* dwl, float* db,
                              float* demb, void* stream) {
+  dvd::ProfScope _ps(3, "dhead_bwd", dvd::as_stream(stream));
   DVD_CHECK_ARG(x && feat && dout && w_lin && sigma_l && emb && sigma_e && class_id && dx && dwl && db && demb);
   DVD_CHECK_ARG(N > 0 && C > 0 && HW > 0 && T > 0 && n_class > 0);
   cudaStream_t st = as_stream(stream);
@@ -537,6 +643,7 @@ extern "C" int dvd_dhead_bwd(const float* x, const float* feat, const float* dou
 }
 extern "C" int dvd_gan_loss_fwd(const float* x, int n, float sign, int hinge, int accumulate, float* loss,
                                 void* stream) {
+  dvd::ProfScope _ps(3, "gan_loss_fwd", dvd::as_stream(stream));
   DVD_CHECK_ARG(x && loss && n > 0);
   gan_loss_fwd_kernel<<<1, 1024, 0, as_stream(stream)>>>(x, n, sign, hinge, accumulate, loss);
   DVD_LAUNCH_CHECK();
@@ -544,6 +651,7 @@ extern "C" int dvd_gan_loss_fwd(const float* x, int n, float sign, int hinge, in
 }
 extern "C" int dvd_gan_loss_bwd(const float* x, const float* gout, int n, float sign, int hinge, float* dx,
                                 void* stream) {
+  dvd::ProfScope _ps(3, "gan_loss_bwd", dvd::as_stream(stream));
   DVD_CHECK_ARG(x && gout && dx && n > 0);
   gan_loss_bwd_kernel<<<ew_blocks(n, 1), 256, 0, as_stream(stream)>>>(x, gout, n, sign, hinge, dx);
   DVD_LAUNCH_CHECK();
@@ -551,6 +659,7 @@ extern "C" int dvd_gan_loss_bwd(const float* x, const float* gout, int n, float 
 }
 extern "C" int dvd_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
                              float beta2, float eps, int step, float grad_scale, void* stream) {
+  dvd::ProfScope _ps(3, "adam_step", dvd::as_stream(stream));
   DVD_CHECK_ARG(p && g && m && v && n > 0 && step >= 1);
   const double bc1 = 1.0 - pow((double)beta1, (double)step);
   const double bc2 = 1.0 - pow((double)beta2, (double)step);

@@ -256,12 +256,251 @@ __global__ void cbn_bwd_dx_kernel(const float* __restrict__ x, const float* __re
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// vectorised plane walkers (the layouts the model uses: H*W % 4 == 0, W even).  A plane = one (n, c) image of H*W
+// floats; `lpp` lanes (a power of two <= 32) share a plane, 32/lpp planes per warp pass, so 4x4 planes still fill a
+// warp.  Per-plane parameters are read once per plane; no per-element integer division; 128-bit loads / stores.
+// ------------------------------------------------------------------------------------------------
+struct PlaneWalk {
+  int lane, lpp, ppw, sub, l;
+  int64_t first, stride;
+  __device__ PlaneWalk(int lanes_per_plane) {
+    lane = threadIdx.x & 31;
+    lpp = lanes_per_plane;
+    ppw = 32 / lpp;
+    sub = lane / lpp;
+    l = lane - sub * lpp;
+    const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    first = warp * ppw + sub;
+    stride = (int64_t)gridDim.x * (blockDim.x >> 5) * ppw;
+  }
+};
+
+__global__ void bn_partial_vec_kernel(const float* __restrict__ x, int N, int C, int HW, int n_per_block,
+                                      double* __restrict__ acc /* [2C] */) {
+  __shared__ double red[32];
+  const int c = blockIdx.x;
+  const int nb = blockIdx.y * n_per_block;
+  int ne = nb + n_per_block;
+  if (ne > N) ne = N;
+  double s = 0.0, ss = 0.0;
+  const int HW4 = HW >> 2;
+  if (HW4 >= (int)blockDim.x) {
+    for (int n = nb; n < ne; ++n) {
+      const float4* r4 = reinterpret_cast<const float4*>(x + ((int64_t)n * C + c) * HW);
+      float a = 0.f, b = 0.f;
+      for (int i = threadIdx.x; i < HW4; i += blockDim.x) {
+        const float4 v = __ldg(r4 + i);
+        a += (v.x + v.y) + (v.z + v.w);
+        b += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+      }
+      s += (double)a;
+      ss += (double)b;
+    }
+  } else {
+    // short planes: threads laid out as (planes per pass) x HW4
+    const int rpp = blockDim.x / HW4;
+    const int r = threadIdx.x / HW4, q = threadIdx.x - r * HW4;
+    if (r < rpp) {
+      for (int n = nb + r; n < ne; n += rpp) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(x + ((int64_t)n * C + c) * HW) + q);
+        s += (double)((v.x + v.y) + (v.z + v.w));
+        ss += (double)((v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w));
+      }
+    }
+  }
+  s = block_sum(s, red);
+  ss = block_sum(ss, red);
+  if (threadIdx.x == 0) {
+    atomicAdd(acc + c, s);
+    atomicAdd(acc + C + c, ss);
+  }
+}
+
+template <bool UP>
+__global__ void cbn_apply_vec_kernel(const float* __restrict__ x, const float* __restrict__ gb, int R,
+                                     const float* __restrict__ mean, const float* __restrict__ rstd, int64_t planes,
+                                     int C, int H, int W, int relu, int lpp, float* __restrict__ y) {
+  const PlaneWalk pw(lpp);
+  const int HW = H * W;
+  const int Wh = W >> 1, Wo = W << 1;
+  for (int64_t plane = pw.first; plane < planes; plane += pw.stride) {
+    const int c = (int)(plane % C);
+    const int n = (int)(plane / C);
+    const int r = n % R;
+    const float g = __ldg(gb + (int64_t)r * 2 * C + c), b = __ldg(gb + (int64_t)r * 2 * C + C + c);
+    const float mu = __ldg(mean + c), rs = __ldg(rstd + c);
+    auto f = [&](float v) {
+      v = g * ((v - mu) * rs) + b;
+      return relu ? fmaxf(v, 0.f) : v;
+    };
+    const float* xp = x + plane * HW;
+    if (!UP) {
+      const float4* x4 = reinterpret_cast<const float4*>(xp);
+      float4* y4 = reinterpret_cast<float4*>(y + plane * HW);
+      for (int i = pw.l; i < (HW >> 2); i += pw.lpp) {
+        const float4 v = __ldg(x4 + i);
+        y4[i] = make_float4(f(v.x), f(v.y), f(v.z), f(v.w));
+      }
+    } else {
+      const float2* x2 = reinterpret_cast<const float2*>(xp);
+      float* yp = y + plane * ((int64_t)HW << 2);
+      for (int i = pw.l; i < (HW >> 1); i += pw.lpp) {
+        const int yy = i / Wh, xq = i - yy * Wh;
+        const float2 v = __ldg(x2 + i);
+        const float a = f(v.x), bb = f(v.y);
+        const float4 o = make_float4(a, a, bb, bb);
+        float* row = yp + (int64_t)(2 * yy) * Wo + 4 * xq;
+        *reinterpret_cast<float4*>(row) = o;
+        *reinterpret_cast<float4*>(row + Wo) = o;
+      }
+    }
+  }
+}
+
+// sum over the lanes that share a plane
+__device__ __forceinline__ float group_sum(float v, int lpp) {
+  for (int o = lpp >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <bool UP>
+__global__ void cbn_bwd_plane_vec_kernel(const float* __restrict__ x, const float* __restrict__ gb, int R,
+                                         const float* __restrict__ mean, const float* __restrict__ rstd,
+                                         const float* __restrict__ dy, int64_t planes, int N, int C, int H, int W,
+                                         int relu, int lpp, float* __restrict__ dgb) {
+  const PlaneWalk pw(lpp);
+  const int HW = H * W;
+  const int Wh = W >> 1, Wo = W << 1;
+  // every lane runs the same number of passes (the group reduction is warp-wide)
+  const int64_t base0 = pw.first - pw.sub;
+  for (int64_t base = base0; base < planes; base += pw.stride) {
+    const int64_t plane = base + pw.sub;
+    const bool live = plane < planes;
+    float sg = 0.f, sgx = 0.f;
+    int c = 0, r = 0;
+    if (live) {
+      c = (int)(plane % C);
+      const int n = (int)(plane / C);
+      r = n % R;
+      const float g = __ldg(gb + (int64_t)r * 2 * C + c), b = __ldg(gb + (int64_t)r * 2 * C + C + c);
+      const float mu = __ldg(mean + c), rs = __ldg(rstd + c);
+      auto acc = [&](float xv, float d) {
+        const float xh = (xv - mu) * rs;
+        if (relu && !(g * xh + b > 0.f)) d = 0.f;
+        sg += d;
+        sgx = fmaf(d, xh, sgx);
+      };
+      const float* xp = x + plane * HW;
+      if (!UP) {
+        const float4* x4 = reinterpret_cast<const float4*>(xp);
+        const float4* d4 = reinterpret_cast<const float4*>(dy + plane * HW);
+        for (int i = pw.l; i < (HW >> 2); i += pw.lpp) {
+          const float4 v = __ldg(x4 + i), d = __ldg(d4 + i);
+          acc(v.x, d.x); acc(v.y, d.y); acc(v.z, d.z); acc(v.w, d.w);
+        }
+      } else {
+        const float2* x2 = reinterpret_cast<const float2*>(xp);
+        const float* dp = dy + plane * ((int64_t)HW << 2);
+        for (int i = pw.l; i < (HW >> 1); i += pw.lpp) {
+          const int yy = i / Wh, xq = i - yy * Wh;
+          const float2 v = __ldg(x2 + i);
+          const float* row = dp + (int64_t)(2 * yy) * Wo + 4 * xq;
+          const float4 q0 = __ldg(reinterpret_cast<const float4*>(row));
+          const float4 q1 = __ldg(reinterpret_cast<const float4*>(row + Wo));
+          acc(v.x, (q0.x + q0.y) + (q1.x + q1.y));
+          acc(v.y, (q0.z + q0.w) + (q1.z + q1.w));
+        }
+      }
+    }
+    sg = group_sum(sg, pw.lpp);
+    sgx = group_sum(sgx, pw.lpp);
+    if (live && pw.l == 0) {
+      if (R == N) {
+        dgb[(int64_t)r * 2 * C + c] = sgx;
+        dgb[(int64_t)r * 2 * C + C + c] = sg;
+      } else {
+        atomicAdd(dgb + (int64_t)r * 2 * C + c, sgx);
+        atomicAdd(dgb + (int64_t)r * 2 * C + C + c, sg);
+      }
+    }
+  }
+}
+
+template <bool UP>
+__global__ void cbn_bwd_dx_vec_kernel(const float* __restrict__ x, const float* __restrict__ gb, int R,
+                                      const float* __restrict__ mean, const float* __restrict__ rstd,
+                                      const float* __restrict__ dy, const float* __restrict__ m, int64_t planes, int C,
+                                      int H, int W, int relu, int training, int lpp, float* __restrict__ dx) {
+  const PlaneWalk pw(lpp);
+  const int HW = H * W;
+  const int Wh = W >> 1, Wo = W << 1;
+  for (int64_t plane = pw.first; plane < planes; plane += pw.stride) {
+    const int c = (int)(plane % C);
+    const int n = (int)(plane / C);
+    const int r = n % R;
+    const float g = __ldg(gb + (int64_t)r * 2 * C + c), b = __ldg(gb + (int64_t)r * 2 * C + C + c);
+    const float mu = __ldg(mean + c), rs = __ldg(rstd + c);
+    const float m1 = training ? __ldg(m + c) : 0.f, m2 = training ? __ldg(m + C + c) : 0.f;
+    auto f = [&](float xv, float d) {
+      const float xh = (xv - mu) * rs;
+      if (relu && !(g * xh + b > 0.f)) d = 0.f;
+      float v = d * g;
+      if (training) v = v - m1 - xh * m2;
+      return v * rs;
+    };
+    const float* xp = x + plane * HW;
+    if (!UP) {
+      const float4* x4 = reinterpret_cast<const float4*>(xp);
+      const float4* d4 = reinterpret_cast<const float4*>(dy + plane * HW);
+      float4* o4 = reinterpret_cast<float4*>(dx + plane * HW);
+      for (int i = pw.l; i < (HW >> 2); i += pw.lpp) {
+        const float4 v = __ldg(x4 + i), d = __ldg(d4 + i);
+        o4[i] = make_float4(f(v.x, d.x), f(v.y, d.y), f(v.z, d.z), f(v.w, d.w));
+      }
+    } else {
+      const float2* x2 = reinterpret_cast<const float2*>(xp);
+      const float* dp = dy + plane * ((int64_t)HW << 2);
+      float2* o2 = reinterpret_cast<float2*>(dx + plane * HW);
+      for (int i = pw.l; i < (HW >> 1); i += pw.lpp) {
+        const int yy = i / Wh, xq = i - yy * Wh;
+        const float2 v = __ldg(x2 + i);
+        const float* row = dp + (int64_t)(2 * yy) * Wo + 4 * xq;
+        const float4 q0 = __ldg(reinterpret_cast<const float4*>(row));
+        const float4 q1 = __ldg(reinterpret_cast<const float4*>(row + Wo));
+        o2[i] = make_float2(f(v.x, (q0.x + q0.y) + (q1.x + q1.y)), f(v.y, (q0.z + q0.w) + (q1.z + q1.w)));
+      }
+    }
+  }
+}
+
+// lanes per plane for `vecs` vectors per plane: the smallest power of two >= vecs, capped at 32
+static int lanes_per_plane(int vecs) {
+  int l = 1;
+  while (l < vecs && l < 32) l <<= 1;
+  return l;
+}
+static bool vec_ok(const void* a, const void* b, const void* c, int H, int W, int up) {
+  const int HW = H * W;
+  const auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  if (!al(a) || !al(b) || (c && !al(c))) return false;
+  return up ? (W % 2 == 0 && HW % 2 == 0) : (HW % 4 == 0);
+}
+static int walker_blocks(int64_t planes, int lpp) {
+  const int64_t warps = ceil_div<int64_t>(planes, 32 / lpp);
+  const int64_t want = ceil_div<int64_t>(warps, 8);
+  const int64_t cap = (int64_t)num_sms() * 16;
+  return (int)(want < cap ? (want < 1 ? 1 : want) : cap);
+}
+
 }  // namespace dvd
 
 using namespace dvd;
 
 extern "C" int dvd_specnorm_fwd(const float* w_bar, int rows, int cols, float* u, float* v, float* sigma,
                                 float* scratch, void* stream) {
+  dvd::ProfScope _ps(3, "specnorm_fwd", dvd::as_stream(stream));
   DVD_CHECK_ARG(w_bar && u && v && sigma && scratch && rows > 0 && cols > 0);
   cudaStream_t st = as_stream(stream);
   float* vraw = scratch;
@@ -278,6 +517,7 @@ extern "C" int dvd_specnorm_fwd(const float* w_bar, int rows, int cols, float* u
 extern "C" int dvd_specnorm_bwd(const float* g, const float* w_bar, const float* u, const float* v,
                                 const float* sigma, int rows, int cols, float* dw_bar, int accumulate, void* scratch,
                                 void* stream) {
+  dvd::ProfScope _ps(3, "specnorm_bwd", dvd::as_stream(stream));
   DVD_CHECK_ARG(g && w_bar && u && v && sigma && dw_bar && scratch && rows > 0 && cols > 0);
   cudaStream_t st = as_stream(stream);
   double* dot = reinterpret_cast<double*>(scratch);
@@ -293,6 +533,7 @@ extern "C" int dvd_specnorm_bwd(const float* g, const float* w_bar, const float*
 extern "C" int dvd_bn_stats(const float* x, int N, int C, int HW, int training, float momentum, float eps,
                             float* running_mean, float* running_var, int64_t* num_batches_tracked, float* mean,
                             float* rstd, void* scratch, void* stream) {
+  dvd::ProfScope _ps(3, "bn_stats", dvd::as_stream(stream));
   DVD_CHECK_ARG(x && mean && rstd && scratch && N > 0 && C > 0 && HW > 0);
   DVD_CHECK_ARG(training || (running_mean && running_var));
   cudaStream_t st = as_stream(stream);
@@ -305,7 +546,10 @@ extern "C" int dvd_bn_stats(const float* x, int N, int C, int HW, int training, 
     if (splits < 1) splits = 1;
     const int npb = ceil_div(N, splits);
     splits = ceil_div(N, npb);
-    bn_partial_kernel<<<dim3(C, splits), 256, 0, st>>>(x, N, C, HW, npb, acc);
+    if (HW % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (HW >> 2) <= 256 * 1024)
+      bn_partial_vec_kernel<<<dim3(C, splits), 256, 0, st>>>(x, N, C, HW, npb, acc);
+    else
+      bn_partial_kernel<<<dim3(C, splits), 256, 0, st>>>(x, N, C, HW, npb, acc);
     DVD_LAUNCH_CHECK();
   }
   bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, st>>>(acc, C, (double)N * HW, training, momentum, eps, running_mean,
@@ -317,10 +561,19 @@ extern "C" int dvd_bn_stats(const float* x, int N, int C, int HW, int training, 
 
 extern "C" int dvd_cbn_apply(const float* x, const float* gb, int gb_rows, const float* mean, const float* rstd, int N,
                              int C, int H, int W, int relu, int up, float* y, void* stream) {
+  dvd::ProfScope _ps(3, "cbn_apply", dvd::as_stream(stream));
   DVD_CHECK_ARG(x && gb && mean && rstd && y && N > 0 && C > 0 && H > 0 && W > 0 && (up == 0 || up == 1));
   DVD_CHECK_ARG(gb_rows > 0 && gb_rows <= N);
   const int64_t total = ((int64_t)N * C * H * W) << (2 * up);
-  cbn_apply_kernel<<<ew_blocks(total, 4), 256, 0, as_stream(stream)>>>(x, gb, gb_rows, mean, rstd, N, C, H, W, relu, up, y);
+  if (vec_ok(x, y, nullptr, H, W, up)) {
+    const int64_t planes = (int64_t)N * C;
+    const int lpp = lanes_per_plane(up ? (H * W) >> 1 : (H * W) >> 2);
+    const int nb = walker_blocks(planes, lpp);
+    if (up) cbn_apply_vec_kernel<true><<<nb, 256, 0, as_stream(stream)>>>(x, gb, gb_rows, mean, rstd, planes, C, H, W, relu, lpp, y);
+    else cbn_apply_vec_kernel<false><<<nb, 256, 0, as_stream(stream)>>>(x, gb, gb_rows, mean, rstd, planes, C, H, W, relu, lpp, y);
+  } else {
+    cbn_apply_kernel<<<ew_blocks(total, 4), 256, 0, as_stream(stream)>>>(x, gb, gb_rows, mean, rstd, N, C, H, W, relu, up, y);
+  }
   DVD_LAUNCH_CHECK();
   return 0;
 }
@@ -328,20 +581,34 @@ extern "C" int dvd_cbn_apply(const float* x, const float* gb, int gb_rows, const
 extern "C" int dvd_cbn_bwd(const float* x, const float* gb, int gb_rows, const float* mean, const float* rstd,
                            const float* dy, int N, int C, int H, int W, int relu, int up, int training, float* dx,
                            float* dgb, float* scratch, void* stream) {
+  dvd::ProfScope _ps(3, "cbn_bwd", dvd::as_stream(stream));
   DVD_CHECK_ARG(x && gb && mean && rstd && dy && dx && dgb && scratch && N > 0 && C > 0 && (up == 0 || up == 1));
   DVD_CHECK_ARG(gb_rows > 0 && gb_rows <= N);
   cudaStream_t st = as_stream(stream);
   if (gb_rows != N) DVD_CUDA(cudaMemsetAsync(dgb, 0, sizeof(float) * (size_t)gb_rows * 2 * C, st));
   const int64_t planes = (int64_t)N * C;
-  cbn_bwd_plane_kernel<<<(unsigned)ceil_div<int64_t>(planes, 8), 256, 0, st>>>(x, gb, gb_rows, mean, rstd, dy, N, C, H, W,
-                                                                             relu, up, dgb);
+  const bool vec = vec_ok(x, dy, dx, H, W, up);
+  const int lpp = lanes_per_plane(up ? (H * W) >> 1 : (H * W) >> 2);
+  const int nb = walker_blocks(planes, lpp);
+  if (vec) {
+    if (up) cbn_bwd_plane_vec_kernel<true><<<nb, 256, 0, st>>>(x, gb, gb_rows, mean, rstd, dy, planes, N, C, H, W, relu, lpp, dgb);
+    else cbn_bwd_plane_vec_kernel<false><<<nb, 256, 0, st>>>(x, gb, gb_rows, mean, rstd, dy, planes, N, C, H, W, relu, lpp, dgb);
+  } else {
+    cbn_bwd_plane_kernel<<<(unsigned)ceil_div<int64_t>(planes, 8), 256, 0, st>>>(x, gb, gb_rows, mean, rstd, dy, N, C, H,
+                                                                               W, relu, up, dgb);
+  }
   DVD_LAUNCH_CHECK();
   if (training) {
     cbn_bwd_chan_kernel<<<C, 256, 0, st>>>(gb, dgb, gb_rows, C, 1.f / ((float)N * H * W), scratch);
     DVD_LAUNCH_CHECK();
   }
-  cbn_bwd_dx_kernel<<<ew_blocks(planes * H * W, 4), 256, 0, st>>>(x, gb, gb_rows, mean, rstd, dy, scratch, N, C, H, W, relu,
-                                                                  up, training, dx);
+  if (vec) {
+    if (up) cbn_bwd_dx_vec_kernel<true><<<nb, 256, 0, st>>>(x, gb, gb_rows, mean, rstd, dy, scratch, planes, C, H, W, relu, training, lpp, dx);
+    else cbn_bwd_dx_vec_kernel<false><<<nb, 256, 0, st>>>(x, gb, gb_rows, mean, rstd, dy, scratch, planes, C, H, W, relu, training, lpp, dx);
+  } else {
+    cbn_bwd_dx_kernel<<<ew_blocks(planes * H * W, 4), 256, 0, st>>>(x, gb, gb_rows, mean, rstd, dy, scratch, N, C, H, W,
+                                                                    relu, up, training, dx);
+  }
   DVD_LAUNCH_CHECK();
   return 0;
 }

@@ -223,6 +223,48 @@ def test_convgru_cell(dev, golden, name, cfg):
     assert rel(x.grad, fx["dx"]) < GRAD_TOL and rel(h.grad, fx["dh"]) < GRAD_TOL
 
 
+@pytest.mark.parametrize("shape", [
+    (8, 4, 64, 64, 16, 16, 3),          # one CTA per tile
+    (4, 3, 32, 96, 16, 16, 5),          # Cx != Ch, 5x5, hidden planes padded 96 -> 128 channels
+    (48, 3, 128, 128, 32, 32, 3),       # more than a wave: CTA-pair tiles
+])
+def test_convgru_layer_tensor_path(dev, shape):
+    """A ConvGRU layer wide enough for the tcgen05 engine (gate math fused into the GEMM epilogues, fp16 operand
+    planes handed from step to step) against the cell equations of ConvGRU.py:47-52 in plain torch fp32."""
+    from dvdgan_b200.Module.ConvGRU import ConvGRUCell
+    B, T, Cx, Ch, H, W, k = shape
+    torch.manual_seed(sum(shape))
+    cell = ConvGRUCell(Cx, Ch, k)
+    for p in cell.parameters():
+        if p.dim() == 1:
+            p.data.normal_(0, 0.1)
+    x = (torch.randn(B, T, Cx, H, W) * 0.7).requires_grad_(True)
+    gy = torch.randn(B, T, Ch, H, W)
+    h, outs = None, []
+    for t in range(T):
+        hp = torch.zeros(B, Ch, H, W) if h is None else h
+        s_ = torch.cat([x[:, t], hp], 1)
+        u = torch.sigmoid(F.conv2d(s_, cell.update_gate.weight, cell.update_gate.bias, padding=k // 2))
+        r = torch.sigmoid(F.conv2d(s_, cell.reset_gate.weight, cell.reset_gate.bias, padding=k // 2))
+        o = torch.tanh(F.conv2d(torch.cat([x[:, t], hp * r], 1), cell.out_gate.weight, cell.out_gate.bias,
+                                padding=k // 2))
+        h = hp * (1 - u) + o * u
+        outs.append(h)
+    y_ref = torch.stack(outs, 1)
+    y_ref.backward(gy)
+    ref_grads = {n: p.grad.clone() for n, p in cell.named_parameters()}
+    dx_ref = x.grad.clone()
+    cell.zero_grad()
+    cell.to(dev)
+    xg = x.detach().to(dev).requires_grad_(True)
+    y = cell.sequence(xg)
+    assert rel(y, y_ref) < FWD_TOL
+    y.backward(gy.to(dev))
+    assert rel(xg.grad, dx_ref) < GRAD_TOL
+    for n, p in cell.named_parameters():
+        assert rel(p.grad, ref_grads[n]) < GRAD_TOL, (n, rel(p.grad, ref_grads[n]))
+
+
 def test_convgru_sequence(dev, golden):
     from dvdgan_b200.Module.ConvGRU import ConvGRU
     fx = golden("blocks.pt")["gru_seq"]
