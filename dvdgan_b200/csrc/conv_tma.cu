@@ -24,6 +24,7 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
+#include <algorithm>
 #include <mutex>
 
 #include "common.cuh"
@@ -409,13 +410,17 @@ __device__ __forceinline__ void collect_promoted(const Bars<STAGES>& bars, uint3
 // 128 rows of A and HALF of the BN weight rows, rank 0 issues tcgen05.mma.cta_group::2 (M = 256) and each CTA's TMEM
 // receives its 128 accumulator rows.  The pair exists because the main loop is bound by the bytes an SM can pull in
 // per cycle (64 KB of planes per 128x128x64 k-block = 3 MMAs per 4 bytes): halving the B bytes per SM is the lever.
-template <int BN, bool PROMOTE, int CG = 1>
+// OCC = 2: two CTAs per SM (two-stage rings, <= 168 registers, 2 * BN <= 256 TMEM columns each) for short-K
+// convolutions, where one CTA's prologue / epilogue would otherwise leave the tensor pipe idle: the co-resident CTA's
+// main loop runs underneath it.
+template <int BN, bool PROMOTE, int CG = 1, int OCC = 1>
 struct Cfg {
   static constexpr int A_BYTES = BM * 128;
   static constexpr int B_BYTES = (BN / CG) * 128;
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
-  static constexpr int STAGES_FIT = (200 * 1024) / STAGE_BYTES;
+  static constexpr int STAGES_FIT = (OCC == 2 ? 108 * 1024 : 200 * 1024) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_FIT > 5 ? 5 : STAGES_FIT;
+  static_assert(OCC == 1 || (!PROMOTE && BN <= 128), "two CTAs per SM share 512 TMEM columns");
   static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 256;
   static constexpr int TMEM_COLS = tmem_cols_for(PROMOTE ? 3 * BN : 2 * BN);
   static_assert(!PROMOTE || BN <= 128, "promotion needs three accumulator regions");
@@ -454,12 +459,12 @@ __device__ __forceinline__ void store_planes32(__half* hi, __half* lo, const flo
   }
 }
 
-template <int BN, bool PROMOTE, int CG>
-__global__ void __launch_bounds__(NT, 1)
+template <int BN, bool PROMOTE, int CG, int OCC>
+__global__ void __launch_bounds__(NT, OCC)
 conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                     const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                     const FwdP fp) {
-  using C = Cfg<BN, PROMOTE, CG>;
+  using C = Cfg<BN, PROMOTE, CG, OCC>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const Bars<C::STAGES> bars{reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES)};
@@ -1037,13 +1042,13 @@ static int prep_planes(const float* src, int N1, int N2, int C, int Cp, int64_t 
   return 0;
 }
 
-template <int BN, bool PROMOTE, int CG>
+template <int BN, bool PROMOTE, int CG, int OCC = 1>
 static int launch_fwd(const CUtensorMap* m, const FwdP& fp, dim3 grid, cudaStream_t st) {
-  using C = Cfg<BN, PROMOTE, CG>;
+  using C = Cfg<BN, PROMOTE, CG, OCC>;
   static bool configured = false;
   if (!configured) {
-    DVD_CUDA(cudaFuncSetAttribute(conv_tma_fwd_kernel<BN, PROMOTE, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  C::SMEM));
+    DVD_CUDA(cudaFuncSetAttribute(conv_tma_fwd_kernel<BN, PROMOTE, CG, OCC>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
     configured = true;
   }
   const int cx = CG == 2 ? 2 : fp.cm, cy = CG == 2 ? 1 : fp.cn;
@@ -1054,9 +1059,9 @@ static int launch_fwd(const CUtensorMap* m, const FwdP& fp, dim3 grid, cudaStrea
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = cx; attr[0].val.clusterDim.y = cy; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    DVD_CUDA(cudaLaunchKernelEx(&cfg, conv_tma_fwd_kernel<BN, PROMOTE, CG>, m[0], m[1], m[2], m[3], fp));
+    DVD_CUDA(cudaLaunchKernelEx(&cfg, conv_tma_fwd_kernel<BN, PROMOTE, CG, OCC>, m[0], m[1], m[2], m[3], fp));
   } else {
-    conv_tma_fwd_kernel<BN, PROMOTE, CG><<<grid, NT, C::SMEM, st>>>(m[0], m[1], m[2], m[3], fp);
+    conv_tma_fwd_kernel<BN, PROMOTE, CG, OCC><<<grid, NT, C::SMEM, st>>>(m[0], m[1], m[2], m[3], fp);
   }
   return 0;
 }
@@ -1276,10 +1281,17 @@ int tma_fwd_launch_ex(ConvP& p, const TmaOperands* ops, const GruEpi* epi, cudaS
   fp.c = p;
   dim3 grid(mt, ceil_div(d.Cout, bn), nsplit);
   prof_tag(pair ? "fwd M%d Ci%d Co%d t%d bn%d pair acc%d" : "fwd M%d Ci%d Co%d t%d bn%d acc%d", p.M, d.Cin, d.Cout,
-           p.taps, bn, d.accumulate + 2 * (nsplit > 1));
+           p.taps, bn, d.accumulate + 2 * (nsplit > 1) + 4 * (fp.gru.mode != 0));
   prof_begin(0, 2.0 * p.M * (double)d.Cout * d.Cin * p.taps, st);
   int rc;
-  if (pair) {
+  // short reductions on narrow tiles: two CTAs per SM (env DVD_TC_OCC2=0 turns it off)
+  static const bool occ2_on = [] { const char* e = getenv("DVD_TC_OCC2"); return !(e && e[0] == '0'); }();
+  const bool occ2 = occ2_on && !promote && !fp.gru.mode && bn <= 128 && p.iters_total <= 40 &&
+                    ctas >= 2 * (int64_t)nsm && (pair || bn == 64);     // (one CTA, 128 wide) stages are 64 KB: no room
+  if (occ2) {
+    if (pair) rc = bn == 128 ? launch_fwd<128, false, 2, 2>(maps, fp, grid, st) : launch_fwd<64, false, 2, 2>(maps, fp, grid, st);
+    else rc = launch_fwd<64, false, 1, 2>(maps, fp, grid, st);
+  } else if (pair) {
     if (bn == 256) rc = launch_fwd<256, false, 2>(maps, fp, grid, st);
     else if (bn == 192) rc = launch_fwd<192, false, 2>(maps, fp, grid, st);
     else if (bn == 128) rc = promote ? launch_fwd<128, true, 2>(maps, fp, grid, st) : launch_fwd<128, false, 2>(maps, fp, grid, st);
@@ -1318,11 +1330,19 @@ int tma_wgrad_launch(ConvP& p, float* dwp, cudaStream_t st) {
   const bool promote = pmode != 0 && bn <= 128;  // k = pixels: every CTA runs hundreds of k-blocks
   const bool pair = pair_enabled() && d.Cin % 256 == 0 && bn >= 128;
   const int64_t base = (int64_t)ceil_div(d.Cin, BM) * ceil_div(d.Cout, bn) * p.taps;
+  // split the pixel range so that the grid fills whole waves of CTAs: among 1..32 splits (>= 2048 pixels each) take
+  // the one with the best wave occupancy, preferring fewer splits on a tie (fewer atomics, longer k loops)
   int nsplit = 1;
-  if (base < 2 * nsm) {
-    nsplit = (int)ceil_div<int64_t>(2 * nsm, base);
-    const int maxs = p.M / 2048 > 0 ? p.M / 2048 : 1;
-    if (nsplit > maxs) nsplit = maxs;
+  {
+    const int maxs = std::max(1, std::min(32, p.M / 2048));
+    double best = -1.0;
+    for (int ns = 1; ns <= maxs; ++ns) {
+      const int64_t ctas = base * ns;
+      const int64_t waves = ceil_div<int64_t>(ctas, nsm);
+      double eff = (double)ctas / (double)(waves * nsm);
+      if (waves < 2) eff *= 0.9;                 // a single (partial) wave exposes the prologue / epilogue
+      if (eff > best + 0.02) { best = eff; nsplit = ns; }
+    }
   }
   int per = ceil_div(p.M, nsplit);
   per = round_up(per, BKC);

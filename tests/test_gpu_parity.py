@@ -90,6 +90,9 @@ CONV_CASES = [
     (1536, 128, 128, 1, 4, 4, (1, 3, 3)),    # 32-row slices = two 4x4 images
     (8, 64, 128, 1, 64, 64, (1, 3, 3)),      # 32-row slices = half an image row
     (4, 64, 128, 8, 32, 32, (3, 3, 3)),      # 3-D, clustered
+    # short reductions on narrow tiles: two co-resident CTAs per SM (CTA pairs, and single CTAs when the tile count is odd)
+    (16, 64, 128, 1, 64, 64, (1, 3, 3)),
+    (33, 64, 64, 1, 36, 32, (1, 3, 3)),
     # 3-channel image convs with >= 2^18 pixels: zero-padded onto the tensor path (fwd, dgrad and wgrad)
     (64, 3, 64, 1, 64, 64, (1, 3, 3)),
     (64, 64, 3, 1, 64, 64, (1, 3, 3)),
