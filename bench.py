@@ -32,6 +32,10 @@ METRIC = "clips/sec (48f x 64x64) G+Ds+Dt step"
 UNIT = "clips/s"
 STEP_TFLOP_PER_CLIP = 8.187     # 3*G_fwd + 9*(Ds_fwd + Dt_fwd), 2*MAC
 STEP_HBM_GB_PER_CLIP = 4.42     # SURVEY.md 8(d), compulsory traffic under ideal fusion, fwd+bwd
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel from the committed `ncu --set full`
+# capture (profiles/): the per-timestep h-half update|reset GEMM of the 32x32 ConvGRU stage, B = 64
+NCU_TRAFFIC_BYTES = None
+NCU_TRAFFIC_OF = None
 
 
 def parse():
@@ -232,7 +236,7 @@ def run_b200(a):
         lib.dvd_prof_dump(a.prof_dump.encode())
     launches = lib.dvd_launch_count() - n0
     prof = {}
-    for cat, name in ((0, "conv_fwd_dgrad"), (1, "conv_wgrad")):
+    for cat, name in ((0, "conv_fwd_dgrad"), (1, "conv_wgrad"), (2, "operand_prep"), (3, "helpers")):
         ms, fl, n = ctypes.c_double(), ctypes.c_double(), ctypes.c_longlong()
         lib.dvd_prof_read(cat, ctypes.byref(ms), ctypes.byref(fl), ctypes.byref(n))
         prof[name] = (ms.value, fl.value, n.value)
@@ -263,15 +267,21 @@ def run_b200(a):
                     "d2h_bytes_per_step": 12},
             "gpu_launches": int(launches),
             "roofline": {
-                "kernel": "conv_fwd_kernel (implicit-GEMM conv forward + dgrad, fp32 FFMA)", "bound": "tensor",
+                "kernel": "conv_tma_fwd_kernel (tcgen05 implicit-GEMM conv forward + dgrad; operands split into two "
+                          "16-bit planes, 3 MMAs per algorithmic MAC, fp32 TMEM accumulators)", "bound": "tensor",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
-                "traffic": None, "peak_source": f"{pk_kind} bf16_tflops_sustained",
+                "mma_tflops": 3.0 * achieved, "mma_frac": 3.0 * achieved / peak if peak else None,
+                "traffic": NCU_TRAFFIC_BYTES, "traffic_of": NCU_TRAFFIC_OF,
+                "peak_source": f"{pk_kind} bf16_tflops_sustained",
                 "launches_per_step": k_n / a.steps, "avg_launch_ms": k_ms / k_n if k_n else None,
                 "share_of_step": k_ms * 1e-3 / sec,
                 "fp32_fma_peak_tflops_at_observed_clock": fma_peak,
                 "frac_of_fp32_fma": achieved / fma_peak if fma_peak else None,
                 "wgrad": {"achieved": w_fl / (w_ms * 1e-3) / 1e12 if w_ms > 0 else 0.0,
                           "share_of_step": w_ms * 1e-3 / sec, "launches_per_step": w_n / a.steps},
+                "breakdown_ms_per_step": {k: v[0] / a.steps for k, v in prof.items()},
+                "operand_prep_gbs": prof["operand_prep"][1] / (prof["operand_prep"][0] * 1e-3) / 1e9
+                if prof["operand_prep"][0] > 0 else None,
                 "step": {"tflops": STEP_TFLOP_PER_CLIP * value / world, "hbm_gbs": STEP_HBM_GB_PER_CLIP * value / world,
                          "hbm_frac": STEP_HBM_GB_PER_CLIP * value / world / pk["hbm_gbs"]},
             },

@@ -752,7 +752,12 @@ long long g_prof_dropped[kProfCats] = {0, 0, 0, 0};
 constexpr size_t kProfMax = 1 << 17;
 }  // namespace
 
+thread_local int g_prof_open[kProfCats] = {-1, -1, -1, -1};   // index of the record the depth-0 prof_end closes
+thread_local int g_prof_depth[kProfCats] = {0, 0, 0, 0};      // brackets of one category may nest (entry points that
+                                                               // call other entry points): only the outermost records
+
 void prof_begin(int cat, double flops, cudaStream_t st) {
+  if (g_prof_depth[cat]++ > 0) return;          // nested bracket of the same category: the outer one covers it
   if (!g_prof_on) return;
   std::lock_guard<std::mutex> lk(g_prof_mu);
   if (g_prof[cat].size() >= kProfMax) { ++g_prof_dropped[cat]; return; }
@@ -763,16 +768,19 @@ void prof_begin(int cat, double flops, cudaStream_t st) {
   memcpy(r.tag, g_prof_tag, sizeof(r.tag));
   cudaEventRecord(r.a, st);
   g_prof[cat].push_back(r);
+  g_prof_open[cat] = (int)g_prof[cat].size() - 1;
 }
 void prof_tag(const char* fmt, int a, int b, int c, int d, int e, int f) {
   if (!g_prof_on) return;
   snprintf(g_prof_tag, sizeof(g_prof_tag), fmt, a, b, c, d, e, f);
 }
 void prof_end(int cat, cudaStream_t st) {
-  if (!g_prof_on) return;
+  if (g_prof_depth[cat] > 0 && --g_prof_depth[cat] > 0) return;
   std::lock_guard<std::mutex> lk(g_prof_mu);
-  if (g_prof[cat].empty() || g_prof_dropped[cat]) return;
-  cudaEventRecord(g_prof[cat].back().b, st);
+  const int i = g_prof_open[cat];
+  if (i < 0) return;
+  if (i < (int)g_prof[cat].size()) cudaEventRecord(g_prof[cat][i].b, st);
+  g_prof_open[cat] = -1;
 }
 }  // namespace dvd
 
@@ -790,11 +798,13 @@ extern "C" int dvd_prof_read(int category, double* ms, double* flops, long long*
   std::lock_guard<std::mutex> lk(dvd::g_prof_mu);
   double t = 0.0, f = 0.0;
   for (auto& r : dvd::g_prof[category]) {
-    DVD_CUDA(cudaEventSynchronize(r.b));
     float e = 0.f;
-    DVD_CUDA(cudaEventElapsedTime(&e, r.a, r.b));
-    t += e;
-    f += r.flops;
+    if (cudaEventSynchronize(r.b) == cudaSuccess && cudaEventElapsedTime(&e, r.a, r.b) == cudaSuccess) {
+      t += e;
+      f += r.flops;
+    } else {
+      cudaGetLastError();      // a bracket that never closed (error path): drop it, do not poison later launches
+    }
     dvd::g_pool.push_back(r);
   }
   *ms = t;
@@ -816,9 +826,9 @@ extern "C" int dvd_prof_dump(const char* path) {
     std::vector<double> ms, fl;
     std::vector<long long> cnt;
     for (auto& r : dvd::g_prof[cat]) {
-      if (cudaEventSynchronize(r.b) != cudaSuccess) continue;
+      if (cudaEventSynchronize(r.b) != cudaSuccess) { cudaGetLastError(); continue; }
       float e = 0.f;
-      if (cudaEventElapsedTime(&e, r.a, r.b) != cudaSuccess) continue;
+      if (cudaEventElapsedTime(&e, r.a, r.b) != cudaSuccess) { cudaGetLastError(); continue; }
       size_t i = 0;
       for (; i < keys.size(); ++i) if (keys[i] == r.tag) break;
       if (i == keys.size()) { keys.push_back(r.tag); ms.push_back(0); fl.push_back(0); cnt.push_back(0); }

@@ -795,8 +795,11 @@ conv_tma_wgrad_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_c
 
   const int ci0 = blockIdx.x * BM;
   const int co0 = blockIdx.y * BN;
-  const int tap = blockIdx.z / wp.nsplit;
-  const int split = blockIdx.z - tap * wp.nsplit;
+  // tap fastest: the CTAs of one wave sweep the SAME pixel range for all taps / channel blocks, so the X and dY planes
+  // come out of L2 for all but the first of them (tap-major order re-read both planes from DRAM once per tap: 24x the
+  // algorithmic bytes in the ncu capture of profiles/)
+  const int split = blockIdx.z / p.taps;
+  const int tap = blockIdx.z - split * p.taps;
   const int m_lo = split * wp.per_split;
   const int m_hi = min(m_lo + wp.per_split, p.M);
   const int n_iters = (m_hi - m_lo + BKC - 1) / BKC;
@@ -1213,6 +1216,10 @@ int tma_fwd_launch_ex(ConvP& p, const TmaOperands* ops, const GruEpi* epi, cudaS
   int bn = pick_bn(d.Cout, pmode == 1 ? 128 : 256, true);
   const int mt = ceil_div(p.M, BM);
   if (bn > 128 && (int64_t)mt * ceil_div(d.Cout, bn) < nsm) bn = 128;        // small grids: more, narrower tiles
+  // short reductions prefer 128-wide tiles with two CTAs per SM over one 256-wide tile (+7 % on the 3x3 convs at
+  // 256 channels; env DVD_TC_SHORTK_BN128=0 turns it off)
+  static const bool shortk128 = [] { const char* e = getenv("DVD_TC_SHORTK_BN128"); return !(e && e[0] == '0'); }();
+  if (shortk128 && bn > 128 && p.iters_total <= 40 && d.Cout % 128 == 0 && !(epi && epi->mode)) bn = 128;
   const bool promote = pmode != 0 && bn <= 128 && p.iters_total > PROMOTE_MIN;
   const bool ext_w = ops && ops->w_hi, ext_a = ops && ops->a_hi;
   const int CoutP = ext_w ? ops->CoutP : round_up(d.Cout, bn);

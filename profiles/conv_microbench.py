@@ -22,6 +22,8 @@ SHAPES = {
     "s0_cell1_h_ur": (64, 512, 1024, 4, 4, 5),
     "s9_cell1_x_all": (768, 128, 768, 32, 32, 5),      # a quarter of the batched x-half (B*T = 3072 frames)
     "gres_64": (512, 128, 64, 64, 64, 3),
+    "gres_32": (3072, 128, 128, 32, 32, 3),           # GResBlock 3x3 convs over all B*T frames (short K)
+    "gres_16": (3072, 256, 256, 16, 16, 3),
 }
 
 
