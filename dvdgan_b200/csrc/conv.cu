@@ -345,6 +345,22 @@ int conv_fwd_ex(const dvd_conv_desc* d, const float* x, const float* w_packed, f
   if (!tma_fwd_launch_ex_eligible(p)) return fail("conv_fwd_ex: shape not eligible%s (%s:%d)", "", __FILE__, __LINE__);
   return tma_fwd_launch_ex(p, ops, epi, st);
 }
+bool conv_wgrad_ex_eligible(const dvd_conv_desc* d, const TmaWgOperands* ops) {
+  if (check_desc(d)) return false;
+  ConvP p;
+  fill_common(p, d);
+  return tma_wgrad_eligible(p) && tma_wgrad_ex_ok(p, ops);
+}
+int conv_wgrad_ex(const dvd_conv_desc* d, const float* x, float* dwp, const TmaWgOperands* ops, cudaStream_t st) {
+  DVD_TRY(check_desc(d));
+  DVD_CHECK_ARG(x && dwp && ops && ops->y_hi && ops->y_lo);
+  ConvP p;
+  fill_common(p, d);
+  p.x = x; p.y = nullptr; p.w = nullptr; p.bias = nullptr; p.res = nullptr;
+  if (!(tma_wgrad_eligible(p) && tma_wgrad_ex_ok(p, ops)))
+    return fail("conv_wgrad_ex: shape not eligible%s (%s:%d)", "", __FILE__, __LINE__);
+  return tma_wgrad_launch_ex(p, dwp, ops, st);
+}
 }  // namespace dvd
 
 using namespace dvd;

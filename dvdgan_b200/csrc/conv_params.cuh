@@ -60,8 +60,25 @@ int tma_split_weights(const float* w_packed, int taps, int Cin, int Cout, int Co
 int tma_split_activations(const float* x, int N, int C, int64_t n_stride, int64_t c_stride, int pix, int fp16, void* hi,
                           void* lo, cudaStream_t st);
 inline int tma_round64(int c) { return (c + 63) / 64 * 64; }
+// stream-ordered scratch (cudaMallocAsync pool of the engine); free with tma_scratch_free on the same stream
+int tma_scratch_alloc(void** p, size_t bytes, cudaStream_t st);
+void tma_scratch_free(void* p, cudaStream_t st);
 bool tma_forward_planes_fp16();   // forward operands are split into fp16 planes (default; env DVD_TC_FMT=bf16 turns it off)
 
+// Pre-split dY planes for the weight-gradient engine: bf16 (hi, lo*2^8) planes [clips*T][D*H*W][Cp] of a (clips, T, C)
+// tensor; the conv's dY is channels [c_off, c_off + Cout) of frames [t_off, t_off + d.N2) of every clip (d.N1 clips).
+struct TmaWgOperands {
+  const void* y_hi = nullptr;
+  const void* y_lo = nullptr;
+  int y_Cp = 0;        // channels per pixel in the planes (multiple of 64)
+  int y_c_off = 0;     // first channel of this conv's dY (multiple of 64)
+  int y_T = 0;         // frames per clip in the planes
+  int y_t_off = 0;     // first frame used
+};
+bool conv_wgrad_ex_eligible(const dvd_conv_desc* d, const TmaWgOperands* ops);
+int conv_wgrad_ex(const dvd_conv_desc* d, const float* x, float* dwp, const TmaWgOperands* ops, cudaStream_t st);
+int tma_split_gradients(const float* g, int N, int C, int64_t n_stride, int64_t c_stride, int pix, void* hi, void* lo,
+                        cudaStream_t st);     // bf16 planes [N][pix][round64(C)]
 bool conv_fwd_ex_eligible(const dvd_conv_desc* d);
 int conv_fwd_ex(const dvd_conv_desc* d, const float* x, const float* w_packed, float* y, const TmaOperands* ops,
                 const GruEpi* epi, cudaStream_t st);
@@ -71,5 +88,7 @@ bool tma_fwd_eligible(const ConvP& p);
 int tma_fwd_launch(ConvP& p, cudaStream_t st);
 bool tma_wgrad_eligible(const ConvP& p);
 int tma_wgrad_launch(ConvP& p, float* dwp, cudaStream_t st);
+bool tma_wgrad_ex_ok(const ConvP& p, const TmaWgOperands* ops);
+int tma_wgrad_launch_ex(ConvP& p, float* dwp, const TmaWgOperands* ops, cudaStream_t st);
 
 }  // namespace dvd

@@ -286,6 +286,8 @@ struct TileGeom {
 
 // ------------------------------------------------------------------------------------------------ shared pieces
 constexpr int CHUNK = 8;       // k-blocks per promoted chunk (8 * 64 / 16 = 32 accumulator adds)
+constexpr int LATE_ITERS = 24; // the epilogue's L2 prefetch starts this many k-blocks before the end of the main loop
+                               // (earlier, the lines are evicted again by the operand stream of a long main loop)
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
@@ -303,12 +305,14 @@ struct Bars {
   __device__ uint64_t* cfull(int b) const { return base + 2 * STAGES + 1 + b; }
   __device__ uint64_t* cdrain(int b) const { return base + 2 * STAGES + 3 + b; }
   __device__ uint32_t* slot() const { return reinterpret_cast<uint32_t*>(base + 2 * STAGES + 5); }
+  __device__ uint64_t* late() const { return base + 2 * STAGES + 6; }     // "the main loop is about to finish"
   __device__ void init(uint32_t empty_count = 1, uint32_t drain_count = 128) const {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(smem_u32(full(s)), 1);
       mbar_init(smem_u32(empty(s)), empty_count);      // one commit per CTA of the cluster that shares the stage
     }
     mbar_init(smem_u32(accum()), 1);
+    mbar_init(smem_u32(late()), 1);
     for (int b = 0; b < 2; ++b) {
       mbar_init(smem_u32(cfull(b)), 1);
       mbar_init(smem_u32(cdrain(b)), drain_count);
@@ -328,6 +332,7 @@ __device__ __forceinline__ void mma_issue_loop(uint8_t* smem, const Bars<STAGES>
   const uint32_t id_main = make_idesc(BN, mn_major, fmt, fmt, BM * CG);
   const uint32_t id_lo1 = id_main, id_lo2 = id_main;
   const uint32_t lo_col = tmem_base + (PROMOTE ? 2 * BN : BN);
+  const int late_it = n_iters > LATE_ITERS ? n_iters - LATE_ITERS : 0;
   int stage = 0;
   uint32_t phase = 0;
   for (int it = 0; it < n_iters; ++it) {
@@ -336,6 +341,10 @@ __device__ __forceinline__ void mma_issue_loop(uint8_t* smem, const Bars<STAGES>
     if (PROMOTE && first && chunk >= 2) {        // the epilogue must have drained this region (chunk - 2)
       mbar_wait(smem_u32(bars.cdrain(chunk & 1)), (uint32_t)(((chunk >> 1) - 1) & 1));
       tc_fence_after();
+    }
+    if (it == late_it) {          // tell the epilogue warps (of both CTAs of a pair) to start prefetching their operands
+      mbar_arrive(smem_u32(bars.late()));
+      if constexpr (CG == 2) mbar_arrive_cluster(mapa_rank(smem_u32(bars.late()), 1));
     }
     mbar_wait(smem_u32(bars.full(stage)), phase);
     tc_fence_after();
@@ -436,6 +445,7 @@ struct FwdP {
   int cm, cn;           // CG = 1 only: cluster = cm m-tiles x cn n-tiles, the A tile is multicast to the cn CTAs of an
                         // m-tile (each loads 1/cn of its rows), the B tile to the cm CTAs of an n-tile
   GruEpi gru;           // ConvGRU gate / state epilogue (mode 0: plain conv epilogue)
+  int prefetch;         // epilogue operands are prefetched into L2 late in the main loop (env DVD_TC_EPI_PREFETCH=0: off)
 };
 
 // 32 consecutive channels of one pixel -> fp16 hi / lo planes (same split as prep_planes_kernel, fp16 = 1)
@@ -678,7 +688,8 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
     };
     // While the main loop runs these warps are idle: pull everything the epilogue will read into L2, so its loads pay
     // an L2 hit instead of a DRAM round trip per 32-channel chunk.
-    if (ok && !p.atomic_out && (d.accumulate || ge.mode)) {
+    if (fp.prefetch && !p.atomic_out && (d.accumulate || ge.mode)) mbar_wait(smem_u32(bars.late()), 0);
+    if (fp.prefetch && ok && !p.atomic_out && (d.accumulate || ge.mode)) {
       const int nb = m / p.DHW, pix = m - nb * p.DHW;
       const int cend = min(BN, d.Cout - n0);
       for (int j = 0; j < cend; ++j) prefetch_l2(p.y + yo + (int64_t)(n0 + j) * d.y_cs);
@@ -736,6 +747,8 @@ struct WgP {
   TileGeom g;           // box of 64 pixels
   int nsplit, per_split;   // pixel range per CTA (multiple of 64)
   int cm, cn;              // cluster = cm ci-blocks x cn co-blocks: the dY tile is multicast across cm, the X tile across cn
+  int y_c_off;             // shared dY planes: channel offset, frames per clip in the planes, first frame, frames used
+  int y_T, y_t_off, y_n2;  // (y_T = 0: the planes hold exactly this conv's images)
 };
 
 template <int BN, bool PROMOTE, int CG = 1>
@@ -824,13 +837,15 @@ conv_tma_wgrad_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_c
         rem -= z0 * p.HW;
         const int y0 = rem / d.W;
         const int x0 = rem - y0 * d.W;
+        // dY may live in planes shared with other convs of the layer: frame t of clip b is image b * y_T + t + y_t_off
+        const int yimg = wp.y_T ? (img / wp.y_n2) * wp.y_T + (img % wp.y_n2) + wp.y_t_off : img;
         mbar_wait(smem_u32(empty_bar + stage), phase ^ 1);
         const uint32_t fb = smem_u32(full_bar + stage);
         const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
         if constexpr (CG == 2) {
           if (leader) mbar_expect_tx(fb, 2 * C::STAGE_BYTES);
           const uint32_t fbl = mapa_rank(fb, 0);
-          const int cob = co0 + (int)cx * (BN / 2);           // this CTA's half of the pair's co range
+          const int cob = wp.y_c_off + co0 + (int)cx * (BN / 2);    // this CTA's half of the pair's co range
 #pragma unroll
           for (int b = 0; b < 2; ++b) {
             tma_load_5d_pair(sa + b * 8192, &tmX_hi, fbl, ci0 + b * 64, x0 + ox, y0 + oy, z0 + oz, img);
@@ -838,8 +853,8 @@ conv_tma_wgrad_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_c
           }
 #pragma unroll
           for (int b = 0; b < C::B_BLOCKS; ++b) {
-            tma_load_5d_pair(sa + 2 * C::A_BYTES + b * 8192, &tmY_hi, fbl, cob + b * 64, x0, y0, z0, img);
-            tma_load_5d_pair(sa + 2 * C::A_BYTES + C::B_BYTES + b * 8192, &tmY_lo, fbl, cob + b * 64, x0, y0, z0, img);
+            tma_load_5d_pair(sa + 2 * C::A_BYTES + b * 8192, &tmY_hi, fbl, cob + b * 64, x0, y0, z0, yimg);
+            tma_load_5d_pair(sa + 2 * C::A_BYTES + C::B_BYTES + b * 8192, &tmY_lo, fbl, cob + b * 64, x0, y0, z0, yimg);
           }
         } else {
           mbar_expect_tx(fb, C::STAGE_BYTES);
@@ -854,12 +869,13 @@ conv_tma_wgrad_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_c
             }
           }
           for (int b = (int)cx * (C::B_BLOCKS / cm); b < ((int)cx + 1) * (C::B_BLOCKS / cm); ++b) {
+            const int yc = wp.y_c_off + co0 + b * 64;
             if (cm > 1) {
-              tma_load_5d_mc(sa + 2 * C::A_BYTES + b * 8192, &tmY_hi, fb, mask_b, co0 + b * 64, x0, y0, z0, img);
-              tma_load_5d_mc(sa + 2 * C::A_BYTES + C::B_BYTES + b * 8192, &tmY_lo, fb, mask_b, co0 + b * 64, x0, y0, z0, img);
+              tma_load_5d_mc(sa + 2 * C::A_BYTES + b * 8192, &tmY_hi, fb, mask_b, yc, x0, y0, z0, yimg);
+              tma_load_5d_mc(sa + 2 * C::A_BYTES + C::B_BYTES + b * 8192, &tmY_lo, fb, mask_b, yc, x0, y0, z0, yimg);
             } else {
-              tma_load_5d(sa + 2 * C::A_BYTES + b * 8192, &tmY_hi, fb, co0 + b * 64, x0, y0, z0, img);
-              tma_load_5d(sa + 2 * C::A_BYTES + C::B_BYTES + b * 8192, &tmY_lo, fb, co0 + b * 64, x0, y0, z0, img);
+              tma_load_5d(sa + 2 * C::A_BYTES + b * 8192, &tmY_hi, fb, yc, x0, y0, z0, yimg);
+              tma_load_5d(sa + 2 * C::A_BYTES + C::B_BYTES + b * 8192, &tmY_lo, fb, yc, x0, y0, z0, yimg);
             }
           }
         }
@@ -1225,6 +1241,8 @@ int tma_fwd_launch_ex(ConvP& p, const TmaOperands* ops, const GruEpi* epi, cudaS
   const int CoutP = ext_w ? ops->CoutP : round_up(d.Cout, bn);
   fp.CoutP = CoutP;
   if (epi) fp.gru = *epi;
+  static const int epi_prefetch = [] { const char* e = getenv("DVD_TC_EPI_PREFETCH"); return (e && e[0] == '0') ? 0 : 1; }();
+  fp.prefetch = epi_prefetch;
   if (fp.gru.mode) DVD_CHECK_ARG(d.accumulate && fp.gru.Ch % 32 == 0 && !d.out_act && !p.res && !p.bias);
   fp.fp16 = (lo_fp16_enabled() && d.x_kind == 1) ? 1 : 0;
   fp.lo_inv = fp.fp16 ? 1.f / kLoScaleFp16 : 1.f / kLoScaleBf16;
@@ -1325,7 +1343,31 @@ bool tma_wgrad_eligible(const ConvP& p) {
   return tma::tile_geom(64, d.N1 * d.N2, d.D, d.H, d.W, &g) && tma::get_encode() != nullptr;
 }
 
-int tma_wgrad_launch(ConvP& p, float* dwp, cudaStream_t st) {
+int tma_scratch_alloc(void** p, size_t bytes, cudaStream_t st) {
+  tma::Scratch sc;
+  DVD_TRY(sc.alloc(bytes, st));
+  *p = sc.ptr;
+  sc.ptr = nullptr;          // ownership passes to the caller
+  return 0;
+}
+void tma_scratch_free(void* p, cudaStream_t st) {
+  if (p) cudaFreeAsync(p, st);
+}
+int tma_split_gradients(const float* g, int N, int C, int64_t n_stride, int64_t c_stride, int pix, void* hi, void* lo,
+                        cudaStream_t st) {
+  return tma::prep_planes(g, N, 1, C, tma_round64(C), n_stride, 0, c_stride, pix, pix, 1, 1, 0, 0, 0,
+                          reinterpret_cast<__nv_bfloat16*>(hi), reinterpret_cast<__nv_bfloat16*>(lo), st);
+}
+int tma_wgrad_launch(ConvP& p, float* dwp, cudaStream_t st) { return tma_wgrad_launch_ex(p, dwp, nullptr, st); }
+// shared dY planes need whole images per 64-pixel box unless they map one to one
+bool tma_wgrad_ex_ok(const ConvP& p, const TmaWgOperands* ops) {
+  if (!ops || !ops->y_hi) return true;
+  if (ops->y_Cp % 64 || ops->y_c_off % 64 || ops->y_c_off + p.d.Cout > ops->y_Cp) return false;
+  const bool identity = ops->y_T == p.d.N2 && ops->y_t_off == 0;
+  return identity || p.DHW % 64 == 0;
+}
+
+int tma_wgrad_launch_ex(ConvP& p, float* dwp, const TmaWgOperands* ops, cudaStream_t st) {
   using namespace tma;
   const dvd_conv_desc& d = p.d;
   const int nsm = num_sms();
@@ -1360,23 +1402,34 @@ int tma_wgrad_launch(ConvP& p, float* dwp, cudaStream_t st) {
   wp.nsplit = nsplit;
   wp.per_split = per;
 
-  const int CinP = round_up(d.Cin, 64), CoutP = round_up(d.Cout, 64);
-  const size_t x_elems = (size_t)N * p.DHW * CinP, y_elems = (size_t)N * p.DHW * CoutP;
+  const bool ext_y = ops && ops->y_hi;
+  const int CinP = round_up(d.Cin, 64), CoutP = ext_y ? ops->y_Cp : round_up(d.Cout, 64);
+  const size_t x_elems = (size_t)N * p.DHW * CinP, y_elems = ext_y ? 0 : (size_t)N * p.DHW * CoutP;
   Scratch sc;
   DVD_TRY(sc.alloc((2 * x_elems + 2 * y_elems) * sizeof(__nv_bfloat16) + 1024, st));
   __nv_bfloat16* x_hi = reinterpret_cast<__nv_bfloat16*>(sc.ptr);
   __nv_bfloat16* x_lo = x_hi + x_elems;
-  __nv_bfloat16* y_hi = x_lo + x_elems;
-  __nv_bfloat16* y_lo = y_hi + y_elems;
+  const __nv_bfloat16 *y_hi, *y_lo;
   DVD_TRY(prep_planes(p.x, d.N1, d.N2, d.Cin, CinP, d.x_s1, d.x_s2, d.x_cs, p.DHW, p.DHW, d.W, p.HW, 0, d.in_relu,
                       0, x_hi, x_lo, st));
-  DVD_TRY(prep_planes(p.y, d.N1, d.N2, d.Cout, CoutP, d.y_s1, d.y_s2, d.y_cs, p.DHW, p.DHW, d.W, p.HW, 0, 0, 0, y_hi,
-                      y_lo, st));
+  int y_images = N;
+  wp.y_c_off = 0; wp.y_T = 0; wp.y_t_off = 0; wp.y_n2 = d.N2;
+  if (ext_y) {
+    y_hi = reinterpret_cast<const __nv_bfloat16*>(ops->y_hi);
+    y_lo = reinterpret_cast<const __nv_bfloat16*>(ops->y_lo);
+    y_images = d.N1 * ops->y_T;
+    wp.y_c_off = ops->y_c_off;
+    if (!(ops->y_T == d.N2 && ops->y_t_off == 0)) { wp.y_T = ops->y_T; wp.y_t_off = ops->y_t_off; }
+  } else {
+    __nv_bfloat16* h = x_lo + x_elems; __nv_bfloat16* l = h + y_elems;
+    DVD_TRY(prep_planes(p.y, d.N1, d.N2, d.Cout, CoutP, d.y_s1, d.y_s2, d.y_cs, p.DHW, p.DHW, d.W, p.HW, 0, 0, 0, h, l, st));
+    y_hi = h; y_lo = l;
+  }
   CUtensorMap maps[4];
   DVD_TRY(make_act_map(&maps[0], x_hi, N, d.D, d.H, d.W, CinP, wp.g));
   DVD_TRY(make_act_map(&maps[1], x_lo, N, d.D, d.H, d.W, CinP, wp.g));
-  DVD_TRY(make_act_map(&maps[2], y_hi, N, d.D, d.H, d.W, CoutP, wp.g));
-  DVD_TRY(make_act_map(&maps[3], y_lo, N, d.D, d.H, d.W, CoutP, wp.g));
+  DVD_TRY(make_act_map(&maps[2], y_hi, y_images, d.D, d.H, d.W, CoutP, wp.g));
+  DVD_TRY(make_act_map(&maps[3], y_lo, y_images, d.D, d.H, d.W, CoutP, wp.g));
   wp.c = p;
   {
     // cluster over (ci-blocks, co-blocks): cm shares the dY tile, cn the X tile

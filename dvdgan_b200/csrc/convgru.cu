@@ -299,17 +299,49 @@ extern "C" int dvd_convgru_layer_bwd(const float* x, int64_t x_bs, int64_t x_ts,
     carry_out = (carry_out == ws.carry0) ? ws.carry1 : ws.carry0;
   }
   if (dh0) DVD_CUDA(cudaMemcpyAsync(dh0, carry_in, sizeof(float) * (size_t)B * chw, cudaMemcpyDeviceToDevice, st));
+  // The pre-activation gradients (da_u | da_r | da_o) of all frames feed four GEMMs (x-dgrad and the three weight
+  // gradients): split them into bf16 planes ONCE and hand the planes to all four (channel / frame offsets in the
+  // TMA coordinates) instead of re-splitting the largest tensor of the layer per GEMM.
+  struct PlanesGuard {
+    void* p = nullptr; cudaStream_t st;
+    ~PlanesGuard() { tma_scratch_free(p, st); }
+  } gp;
+  gp.st = st;
+  TmaWgOperands yo;
+  const int G3P = tma_round64(3 * Ch);
+  dvd_conv_desc d_dx = base_desc(B, T, 3 * Ch, Cx, H, W, k);
+  d_dx.x_s1 = g_bs; d_dx.x_s2 = g_ts; d_dx.y_s1 = (int64_t)T * Cx * HW; d_dx.y_s2 = (int64_t)Cx * HW;
+  dvd_conv_desc d_wx = base_desc(B, T, Cx, 3 * Ch, H, W, k); d_wx.x_kind = 1;
+  d_wx.x_s1 = x_bs; d_wx.x_s2 = x_ts; d_wx.y_s1 = g_bs; d_wx.y_s2 = g_ts;
+  static const bool share_on = [] { const char* e = getenv("DVD_GRU_SHARE_PLANES"); return !(e && e[0] == '0'); }();
+  yo.y_Cp = G3P; yo.y_T = T;
+  bool share = share_on && Ch % 32 == 0 && conv_fwd_ex_eligible(&d_dx);
+  if (share) {
+    yo.y_hi = reinterpret_cast<void*>(1);                     // (eligibility only looks at the geometry)
+    share = conv_wgrad_ex_eligible(&d_wx, &yo);
+    yo.y_hi = nullptr;
+  }
+  if (share) {
+    const size_t elems = (size_t)B * T * HW * G3P;
+    DVD_TRY(tma_scratch_alloc(&gp.p, 2 * elems * sizeof(uint16_t) + 256, st));
+    yo.y_hi = gp.p;
+    yo.y_lo = reinterpret_cast<uint16_t*>(gp.p) + elems;
+    DVD_TRY(tma_split_gradients(gates, B * T, 3 * Ch, g_ts, HW, HW, const_cast<void*>(yo.y_hi), const_cast<void*>(yo.y_lo), st));
+  }
   // dx for all frames: one implicit GEMM over the (da_u | da_r | da_o) buffer
-  {
-    dvd_conv_desc d = base_desc(B, T, 3 * Ch, Cx, H, W, k);
-    d.x_s1 = g_bs; d.x_s2 = g_ts; d.y_s1 = (int64_t)T * Cx * HW; d.y_s2 = (int64_t)Cx * HW;
-    DVD_TRY(dvd_conv_fwd(&d, gates, ws.wxT, nullptr, nullptr, dx, stream));
+  if (share) {
+    TmaOperands op;
+    op.a_hi = yo.y_hi; op.a_lo = yo.y_lo;
+    DVD_TRY(conv_fwd_ex(&d_dx, gates, ws.wxT, dx, &op, nullptr, st));
+  } else {
+    DVD_TRY(dvd_conv_fwd(&d_dx, gates, ws.wxT, nullptr, nullptr, dx, stream));
   }
   // weight gradients, batched over time
-  {
-    dvd_conv_desc d = base_desc(B, T, Cx, 3 * Ch, H, W, k); d.x_kind = 1;
-    d.x_s1 = x_bs; d.x_s2 = x_ts; d.y_s1 = g_bs; d.y_s2 = g_ts;
-    DVD_TRY(dvd_conv_wgrad(&d, x, gates, ws.dwx, stream));
+  if (share) {
+    yo.y_c_off = 0; yo.y_t_off = 0;
+    DVD_TRY(conv_wgrad_ex(&d_wx, x, ws.dwx, &yo, st));
+  } else {
+    DVD_TRY(dvd_conv_wgrad(&d_wx, x, gates, ws.dwx, stream));
   }
   {
     bool have = false;
@@ -317,7 +349,9 @@ extern "C" int dvd_convgru_layer_bwd(const float* x, int64_t x_bs, int64_t x_ts,
       dvd_conv_desc d = base_desc(B, T - 1, Ch, 2 * Ch, H, W, k);   // pairs (h_{t-1}, da_t), t = 1..T-1
       d.x_kind = 1;
       d.x_s1 = h_bs; d.x_s2 = h_ts; d.y_s1 = g_bs; d.y_s2 = g_ts;
-      DVD_TRY(dvd_conv_wgrad(&d, h, gates + g_ts, ws.dwhur, stream));
+      yo.y_c_off = 0; yo.y_t_off = 1;
+      if (share && conv_wgrad_ex_eligible(&d, &yo)) DVD_TRY(conv_wgrad_ex(&d, h, ws.dwhur, &yo, st));
+      else DVD_TRY(dvd_conv_wgrad(&d, h, gates + g_ts, ws.dwhur, stream));
       have = true;
     }
     if (h0) {
@@ -332,7 +366,9 @@ extern "C" int dvd_convgru_layer_bwd(const float* x, int64_t x_bs, int64_t x_ts,
     dvd_conv_desc d = base_desc(B, T, Ch, Ch, H, W, k);             // pairs (rh_t, da_o,t)
     d.x_kind = 1;
     d.x_s1 = h_bs; d.x_s2 = h_ts; d.y_s1 = g_bs; d.y_s2 = g_ts;
-    DVD_TRY(dvd_conv_wgrad(&d, rh, gates + 2 * chw, ws.dwho, stream));
+    yo.y_c_off = 2 * Ch; yo.y_t_off = 0;
+    if (share && conv_wgrad_ex_eligible(&d, &yo)) DVD_TRY(conv_wgrad_ex(&d, rh, ws.dwho, &yo, st));
+    else DVD_TRY(dvd_conv_wgrad(&d, rh, gates + 2 * chw, ws.dwho, stream));
   }
   for (int g = 0; g < 3; ++g) {
     DVD_TRY(dvd_weight_unpack(ws.dwx, 3 * Ch, g * Ch, Ct, taps, 0, Ch, 0, Cx, 0, dwdst[g], stream));

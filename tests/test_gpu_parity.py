@@ -93,6 +93,9 @@ CONV_CASES = [
     # short reductions on narrow tiles: two co-resident CTAs per SM (CTA pairs, and single CTAs when the tile count is odd)
     (16, 64, 128, 1, 64, 64, (1, 3, 3)),
     (33, 64, 64, 1, 36, 32, (1, 3, 3)),
+    # 128- and 256-wide frames (configs 3 and 4): a TMA box is one image row / half an image row
+    (2, 64, 64, 1, 128, 128, (1, 3, 3)),
+    (1, 32, 64, 1, 256, 256, (1, 3, 3)),
     # 3-channel image convs with >= 2^18 pixels: zero-padded onto the tensor path (fwd, dgrad and wgrad)
     (64, 3, 64, 1, 64, 64, (1, 3, 3)),
     (64, 64, 3, 1, 64, 64, (1, 3, 3)),
