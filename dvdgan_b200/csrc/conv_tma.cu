@@ -1379,18 +1379,17 @@ int tma_wgrad_launch_ex(ConvP& p, float* dwp, const TmaWgOperands* ops, cudaStre
   const bool promote = pmode != 0 && bn <= 128;  // k = pixels: every CTA runs hundreds of k-blocks
   const bool pair = pair_enabled() && d.Cin % 256 == 0 && bn >= 128;
   const int64_t base = (int64_t)ceil_div(d.Cin, BM) * ceil_div(d.Cout, bn) * p.taps;
-  // split the pixel range so that the grid fills whole waves of CTAs: among 1..32 splits (>= 2048 pixels each) take
-  // the one with the best wave occupancy, preferring fewer splits on a tie (fewer atomics, longer k loops)
+  // split the pixel range: cost model = waves of CTAs x (k-blocks per CTA + a fixed per-CTA cost of ~40 k-blocks for
+  // the prologue and the atomic epilogue); whole waves matter for the long reductions (M = millions of pixels), the
+  // fixed cost for the short ones
   int nsplit = 1;
   {
     const int maxs = std::max(1, std::min(32, p.M / 2048));
-    double best = -1.0;
+    double best = 1e30;
     for (int ns = 1; ns <= maxs; ++ns) {
-      const int64_t ctas = base * ns;
-      const int64_t waves = ceil_div<int64_t>(ctas, nsm);
-      double eff = (double)ctas / (double)(waves * nsm);
-      if (waves < 2) eff *= 0.9;                 // a single (partial) wave exposes the prologue / epilogue
-      if (eff > best + 0.02) { best = eff; nsplit = ns; }
+      const int64_t waves = ceil_div<int64_t>(base * ns, nsm);
+      const double cost = (double)waves * (ceil_div(ceil_div(p.M, ns), BKC) + 40.0);
+      if (cost < best * 0.99) { best = cost; nsplit = ns; }
     }
   }
   int per = ceil_div(p.M, nsplit);

@@ -96,6 +96,7 @@ struct GruWs {
   uint16_t *whur_hi, *whur_lo, *who_hi, *who_lo;      // [taps][CoutP][ChP]
   uint16_t *hpl_hi[2], *hpl_lo[2];                    // planes of h_{t-1} / h_t (ping-pong), [B*HW][ChP]
   uint16_t *rhpl_hi, *rhpl_lo;                        // planes of r * h_{t-1}
+  uint16_t *whoT_hi, *whoT_lo, *whurT_hi, *whurT_lo;  // backward: [taps][ChP][ChP] / [taps][ChP][round64(2Ch)]
   size_t bytes;
 };
 
@@ -128,6 +129,12 @@ static GruWs carve(void* base, int B, int Cx, int Ch, int HW, int taps, bool bwd
     const size_t pl = (size_t)B * HW * ChP;
     for (int i = 0; i < 2; ++i) { w.hpl_hi[i] = take16(pl); w.hpl_lo[i] = take16(pl); }
     w.rhpl_hi = take16(pl); w.rhpl_lo = take16(pl);
+    if (bwd) {     // bf16 planes of the transposed h-half weights (dgrad operands), split once per layer
+      w.whoT_hi = take16((size_t)taps * ChP * ChP); w.whoT_lo = take16((size_t)taps * ChP * ChP);
+      w.whurT_hi = take16((size_t)taps * ChP * Co2P); w.whurT_lo = take16((size_t)taps * ChP * Co2P);
+    } else {
+      w.whoT_hi = w.whoT_lo = w.whurT_hi = w.whurT_lo = nullptr;
+    }
   }
   w.bytes = off;
   return w;
@@ -277,23 +284,40 @@ extern "C" int dvd_convgru_layer_bwd(const float* x, int64_t x_bs, int64_t x_ts,
   const int eb = ew_blocks((int64_t)B * chw);
   float* carry_in = nullptr;
   float* carry_out = ws.carry0;
+  // the two dgrad GEMMs of a step read the same transposed weights every step: split them into planes once
+  dvd_conv_desc d_rh = base_desc(B, 1, Ch, Ch, H, W, k), d_hp = base_desc(B, 1, 2 * Ch, Ch, H, W, k);
+  d_rh.x_s1 = d_hp.x_s1 = g_bs; d_rh.y_s1 = d_hp.y_s1 = chw; d_hp.accumulate = 1;
+  const int ChP = tma_round64(Ch), Co2P = tma_round64(2 * Ch);
+  const bool wplanes = gru_fused_enabled() && T > 1 && conv_fwd_ex_eligible(&d_rh) && conv_fwd_ex_eligible(&d_hp);
+  if (wplanes) {
+    DVD_TRY(tma_split_weights(ws.whoT, taps, Ch, Ch, ChP, 0, ws.whoT_hi, ws.whoT_lo, st));
+    DVD_TRY(tma_split_weights(ws.whurT, taps, 2 * Ch, Ch, ChP, 0, ws.whurT_hi, ws.whurT_lo, st));
+  }
   for (int t = T - 1; t >= 0; --t) {
     const float* hp = t > 0 ? h + (int64_t)(t - 1) * h_ts : h0;
     const int64_t hp_bs = t > 0 ? h_bs : chw;
     float* g_t = gates + (int64_t)t * g_ts;
     { ProfScope ps(3, "gru_bwd1", st); gru_bwd1_kernel<<<eb, 256, 0, st>>>(g_t, g_bs, hp, hp_bs, dh + (int64_t)t * h_ts, h_bs, carry_in, carry_out, B, chw); }
     DVD_LAUNCH_CHECK();
-    if (hp) {
-      dvd_conv_desc d = base_desc(B, 1, Ch, Ch, H, W, k);     // d(rh) = conv_o^T(da_o), h-half
-      d.x_s1 = g_bs; d.y_s1 = chw;
-      DVD_TRY(dvd_conv_fwd(&d, g_t + 2 * chw, ws.whoT, nullptr, nullptr, ws.d_rh, stream));
+    if (hp) {                                                 // d(rh) = conv_o^T(da_o), h-half
+      if (wplanes) {
+        TmaOperands op;
+        op.w_hi = ws.whoT_hi; op.w_lo = ws.whoT_lo; op.CoutP = ChP;
+        DVD_TRY(conv_fwd_ex(&d_rh, g_t + 2 * chw, ws.whoT, ws.d_rh, &op, nullptr, st));
+      } else {
+        DVD_TRY(dvd_conv_fwd(&d_rh, g_t + 2 * chw, ws.whoT, nullptr, nullptr, ws.d_rh, stream));
+      }
     }
     { ProfScope ps(3, "gru_bwd2", st); gru_bwd2_kernel<<<eb, 256, 0, st>>>(g_t, g_bs, hp, hp_bs, ws.d_rh, carry_out, B, chw); }
     DVD_LAUNCH_CHECK();
-    if (hp) {
-      dvd_conv_desc d = base_desc(B, 1, 2 * Ch, Ch, H, W, k);  // dh_prev += conv_u^T(da_u) + conv_r^T(da_r)
-      d.x_s1 = g_bs; d.y_s1 = chw; d.accumulate = 1;
-      DVD_TRY(dvd_conv_fwd(&d, g_t, ws.whurT, nullptr, nullptr, carry_out, stream));
+    if (hp) {                                                 // dh_prev += conv_u^T(da_u) + conv_r^T(da_r)
+      if (wplanes) {
+        TmaOperands op;
+        op.w_hi = ws.whurT_hi; op.w_lo = ws.whurT_lo; op.CoutP = ChP;
+        DVD_TRY(conv_fwd_ex(&d_hp, g_t, ws.whurT, carry_out, &op, nullptr, st));
+      } else {
+        DVD_TRY(dvd_conv_fwd(&d_hp, g_t, ws.whurT, nullptr, nullptr, carry_out, stream));
+      }
     }
     carry_in = carry_out;
     carry_out = (carry_out == ws.carry0) ? ws.carry1 : ws.carry0;

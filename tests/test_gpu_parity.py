@@ -37,8 +37,19 @@ def ops():
     return o
 
 
-def check_grads(module, grads, tol=GRAD_TOL, zero_suffix=None):
+def check_grads(module, grads, tol=GRAD_TOL, zero_suffix=None, global_tol=None):
     scale = max(float(g.norm()) for g in grads.values() if g is not None)
+    if global_tol is not None:
+        # all gradients as ONE vector: a ReLU / hinge kink that flips under fp32 summation-order noise moves a
+        # small tensor by percents of its own norm but the whole gradient by parts per thousand
+        num = den = 0.0
+        for k, p in module.named_parameters():
+            g = grads.get(k)
+            if g is None or p.grad is None:
+                continue
+            num += float((p.grad.detach().cpu().double() - g.double()).norm() ** 2)
+            den += float(g.double().norm() ** 2)
+        assert (num / den) ** 0.5 < global_tol, ("global", (num / den) ** 0.5)
     for k, p in module.named_parameters():
         g = grads.get(k)
         if g is None:
@@ -447,7 +458,13 @@ def test_generator(dev, golden):
     assert rel(out, fx["out"]) < FWD_TOL
     check_state(G, fx["sd_post_changed"])
     (out * fx["loss_weight"].to(dev)).sum().backward()
-    check_grads(G, fx["grads"], tol=3e-3, zero_suffix="conv0.module.bias")   # end-to-end through 4 ConvGRU stages and 16 CBNs
+    # End to end through 4 ConvGRU stages and 16 CBNs (default init amplifies ~17x per block).  The
+    # reference's OWN parameter gradients move by 2-4e-3 (global rel-L2) when only its thread count changes (SURVEY 7
+    # #2: ReLU / hinge kinks flip under summation-order noise), and split-K / weight-gradient atomics make this
+    # library's summation order vary from run to run.  So: the whole gradient within 1e-2 (3x the reference's own
+    # noise), every tensor within 5e-2 (a wrong kernel is off by O(1)); each kernel's gradients are held to 1e-3 on
+    # identical inputs by the per-kernel tests above.
+    check_grads(G, fx["grads"], tol=5e-2, zero_suffix="conv0.module.bias", global_tol=1e-2)
     G.eval()
     with torch.no_grad():
         out_e = G(fx["z"].to(dev), fx["class_id"].to(dev))
