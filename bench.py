@@ -51,6 +51,8 @@ def parse():
     ap.add_argument("--k-sample", type=int, default=8)
     ap.add_argument("--classes", type=int, default=101)
     ap.add_argument("--ch", type=int, default=32)
+    ap.add_argument("--latent-dim", type=int, default=4, help="frame side = 16 * latent_dim (4: 64x64; 8: configs[2]; "
+                                                             "16: configs[3])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-frames", type=int, default=None, help="debug: shrink the CPU sample")
     ap.add_argument("--prof-dump", default=None, help="write the per-shape launch table of the timed steps here")
@@ -71,7 +73,7 @@ def make_cfg(a, batch):
         adv_loss="hinge", z_dim=120, g_chn=a.ch, ds_chn=a.ch, dt_chn=a.ch, n_frames=a.frames,
         k_sample=a.k_sample, n_class=a.classes, batch_size=batch, d_iters=1, g_lr=5e-5, d_lr=5e-5, beta1=0.0,
         beta2=0.9, lr_schr="const", lr_decay=0.9999, total_epoch=1, log_epoch=10 ** 9, test_batch_size=1,
-        pretrained_model=None, version="bench", model_save_path="/tmp/dvd_bench")
+        pretrained_model=None, version="bench", model_save_path="/tmp/dvd_bench", latent_dim=a.latent_dim)
 
 
 # ----------------------------------------------------------------------------------------------- CPU arm
@@ -87,12 +89,13 @@ def cpu_step_time(a, steps, warmup, frames=None):
     B = 1
     torch.manual_seed(0)
     # random-init weights of the benchmarked architecture (constructors only; the oracle does the math)
-    nets = (Generator(120, 4, a.classes, a.ch, T), SpatialDiscriminator(a.ch, a.classes),
+    nets = (Generator(120, a.latent_dim, a.classes, a.ch, T), SpatialDiscriminator(a.ch, a.classes),
             TemporalDiscriminator(a.ch, a.classes))
     sds = [{k: v.detach().clone() for k, v in n.state_dict().items()} for n in nets]
     tr = O.OracleTrainer(*sds, n_frames=T, k_sample=min(a.k_sample, T), n_class=a.classes, batch_size=B,
-                         g_chn=a.ch, adv_loss="hinge")
-    clip = torch.rand(B, 3, T, 64, 64) * 2 - 1
+                         g_chn=a.ch, adv_loss="hinge", latent_dim=a.latent_dim)
+    side = 16 * a.latent_dim
+    clip = torch.rand(B, 3, T, side, side) * 2 - 1
     lab = torch.randint(0, a.classes, (B,))
     for _ in range(warmup):
         tr.step(clip, lab)
@@ -190,7 +193,8 @@ def run_b200(a):
     tr = Trainer(None, make_cfg(a, B))
     tr.G.train(); tr.D_s.train(); tr.D_t.train()
     n_host = 2
-    host_clips = [(torch.rand(B, 3, T, 64, 64) * 2 - 1).pin_memory() for _ in range(n_host)]
+    side = 16 * a.latent_dim
+    host_clips = [(torch.rand(B, 3, T, side, side) * 2 - 1).pin_memory() for _ in range(n_host)]
     host_labels = [torch.randint(0, a.classes, (B,)).pin_memory() for _ in range(n_host)]
     dev_clips = [c.to(dev) for c in host_clips]
     dev_labels = [l.to(dev) for l in host_labels]
@@ -259,7 +263,7 @@ def run_b200(a):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": sec / a.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"config[1]: {T}f 64x64, {a.classes} classes, batch={B}/GPU, ch={a.ch}, "
+            "config": {"workload": f"config[1]: {T}f {side}x{side}, {a.classes} classes, batch={B}/GPU, ch={a.ch}, "
                                    f"k={a.k_sample}, hinge, Adam(5e-5,(0,0.9)), full G+Ds+Dt step "
                                    "(3 optimizer steps, NCCL grad all-reduce if N>1)",
                        "global_batch": B * world, "l2": "inputs and activations are GBs per step (>> 126 MB L2)",

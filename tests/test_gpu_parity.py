@@ -560,6 +560,45 @@ def test_generator_full_width_vs_oracle(dev):
     assert float((out.cpu() - ref).abs().max()) < 1e-2
 
 
+@pytest.mark.parametrize("cfg", [
+    dict(name="config3: 128x128 frames", ld=8, T=4, B=2, k=2),
+    dict(name="config4: 256x256 frames, N = 4096 attention tokens in Ds", ld=16, T=4, B=1, k=2),
+    dict(name="config5: long clip", ld=4, T=64, B=1, k=8),
+])
+def test_other_config_shapes_vs_oracle(dev, cfg):
+    """BASELINE.json configs 3-5 at reduced width (ch = 8): G -> (Ds on k sampled frames, Dt on the phi-downsampled
+    clip) forward against the CPU oracle -- the frame sizes / clip lengths that change tile geometry, attention
+    length and the depth of the recurrence."""
+    from oracle import dvdgan_oracle as O
+    from dvdgan_b200.Module.Generator import Generator
+    from dvdgan_b200.Module.Discriminators import SpatialDiscriminator, TemporalDiscriminator
+    from dvdgan_b200.utils import vid_downsample
+    torch.manual_seed(11)
+    ld, T, B, k = cfg["ld"], cfg["T"], cfg["B"], cfg["k"]
+    G = Generator(in_dim=120, latent_dim=ld, n_class=5, ch=8, n_frames=T)
+    Ds = SpatialDiscriminator(chn=8, n_class=5)
+    Dt = TemporalDiscriminator(chn=8, n_class=5)
+    for net in (Ds, Dt):
+        for n, p in net.named_parameters():
+            if n.endswith("gamma"):
+                p.data.fill_(0.5)
+    sd_g, sd_s, sd_t = (clone_sd(m.state_dict()) for m in (G, Ds, Dt))
+    z = torch.randn(B, 120)
+    cls = torch.randint(0, 5, (B,))
+    with torch.no_grad():
+        ref = O.generator_forward(sd_g, z, cls, T, 8, ld)
+        ref_s = O.spatial_discriminator(sd_s, ref[:, :k].contiguous(), cls)
+        ref_t = O.temporal_discriminator(sd_t, O.vid_downsample(ref), cls)
+    G.to(dev), Ds.to(dev), Dt.to(dev)
+    with torch.no_grad():
+        out = G(z.to(dev), cls.to(dev))
+        out_s = Ds(out[:, :k].contiguous(), cls.to(dev))
+        out_t = Dt(vid_downsample(out), cls.to(dev))
+    assert out.shape == (B, T, 3, 16 * ld, 16 * ld)
+    assert rel(out, ref) < 1e-3, cfg["name"]
+    assert rel(out_s, ref_s) < 1e-3 and rel(out_t, ref_t) < 1e-3, cfg["name"]
+
+
 def test_discriminators_full_width_vs_oracle(dev):
     """chn=32, k=8 / 48 frames at B=64 on the GPU (configs[1]); the oracle checks a 2-clip slice (frames are
     scored independently, so a slice of the batch is a valid sub-problem)."""
