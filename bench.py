@@ -234,7 +234,9 @@ def run_b200(a):
         step_resident(i)
     sampler = ClockSampler(local) if rank == 0 else None
     n0 = lib.dvd_launch_count()
-    lib.dvd_prof_enable(1)
+    # CUDA events around every GEMM launch (the roofline numbers); with --prof-dump also around every operand split and
+    # helper call (each pair of event records costs ~2 us of stream time, so the default run skips those)
+    lib.dvd_prof_enable(0xF if a.prof_dump else 1)
     sec, w0, w1 = timed(step_resident, a.steps)
     lib.dvd_prof_enable(0)
     if a.prof_dump and rank == 0:          # per-shape table of the GEMM / operand-prep launches of the timed steps
@@ -285,7 +287,7 @@ def run_b200(a):
                 "frac_of_fp32_fma": achieved / fma_peak if fma_peak else None,
                 "wgrad": {"achieved": w_fl / (w_ms * 1e-3) / 1e12 if w_ms > 0 else 0.0,
                           "share_of_step": w_ms * 1e-3 / sec, "launches_per_step": w_n / a.steps},
-                "breakdown_ms_per_step": {k: v[0] / a.steps for k, v in prof.items()},
+                "breakdown_ms_per_step": {k: v[0] / a.steps for k, v in prof.items() if v[2] > 0},
                 "operand_prep_gbs": prof["operand_prep"][1] / (prof["operand_prep"][0] * 1e-3) / 1e9
                 if prof["operand_prep"][0] > 0 else None,
                 "step": {"tflops": STEP_TFLOP_PER_CLIP * value / world, "hbm_gbs": STEP_HBM_GB_PER_CLIP * value / world,

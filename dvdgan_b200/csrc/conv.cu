@@ -760,7 +760,7 @@ namespace {
 struct ProfRec { cudaEvent_t a, b; double flops; char tag[56]; };
 thread_local char g_prof_tag[56] = "";
 std::mutex g_prof_mu;
-bool g_prof_on = false;
+unsigned g_prof_on = 0;            // bit c set: category c is being recorded
 constexpr int kProfCats = 4;       // 0: conv fwd/dgrad GEMM, 1: wgrad GEMM, 2: operand-plane preparation, 3: helpers
 std::vector<ProfRec> g_prof[kProfCats];
 std::vector<ProfRec> g_pool;       // recycled event pairs
@@ -774,7 +774,7 @@ thread_local int g_prof_depth[kProfCats] = {0, 0, 0, 0};      // brackets of one
 
 void prof_begin(int cat, double flops, cudaStream_t st) {
   if (g_prof_depth[cat]++ > 0) return;          // nested bracket of the same category: the outer one covers it
-  if (!g_prof_on) return;
+  if (!(g_prof_on >> cat & 1u)) return;
   std::lock_guard<std::mutex> lk(g_prof_mu);
   if (g_prof[cat].size() >= kProfMax) { ++g_prof_dropped[cat]; return; }
   ProfRec r;
@@ -804,7 +804,8 @@ extern "C" long long dvd_launch_count(void) { return dvd::g_launches.load(); }
 
 extern "C" int dvd_prof_enable(int on) {
   std::lock_guard<std::mutex> lk(dvd::g_prof_mu);
-  dvd::g_prof_on = on != 0;
+  // on = 1: the dense engines only (categories 0, 1); otherwise a bit mask of categories (0xF: everything)
+  dvd::g_prof_on = on == 1 ? 0x3u : (unsigned)on;
   return 0;
 }
 

@@ -469,8 +469,10 @@ __device__ __forceinline__ void store_planes32(__half* hi, __half* lo, const flo
   }
 }
 
-template <int BN, bool PROMOTE, int CG, int OCC>
-__global__ void __launch_bounds__(NT, OCC)
+// EW = epilogue warps: 4 (one per TMEM lane quarter) or 8 (two per quarter, alternating 32-column chunks) -- the
+// wide tiles hold the only accumulator set of the SM, so the tensor pipe idles until the epilogue is through.
+template <int BN, bool PROMOTE, int CG, int OCC, int EW>
+__global__ void __launch_bounds__(64 + 32 * EW, OCC)
 conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                     const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                     const FwdP fp) {
@@ -491,6 +493,7 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
   const uint32_t cx = clustered ? cluster_ctaid_x() : 0u, cy = (clustered && CG == 1) ? cluster_ctaid_y() : 0u;
   const bool leader = CG == 1 || cx == 0;       // pair: rank 0 owns the full barriers and issues the MMAs
 
+  static_assert(EW == 4 || (EW == 8 && !PROMOTE), "the promoted accumulator is drained by exactly four warps");
   if (tid == 0) bars.init(CG == 2 ? 1u : (uint32_t)(cm * cn), CG == 2 ? 256u : 128u);
   if (warp == 1) {
     if constexpr (CG == 2) {
@@ -585,8 +588,10 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
     }
     __syncwarp();
   } else {
-    // ---------------- epilogue: warps 2..5; a warp may only touch TMEM lanes [32*(warp%4), +32)
+    // ---------------- epilogue: warps 2..(EW+1); a warp may only touch TMEM lanes [32*(warp%4), +32); with EW = 8 the
+    // two warps of a quarter take alternate 32-column chunks
     const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int row = q * 32 + lane;
     const int m = m0 + row;
     const bool ok = m < p.M;
@@ -692,9 +697,13 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
     if (fp.prefetch && ok && !p.atomic_out && (d.accumulate || ge.mode)) {
       const int nb = m / p.DHW, pix = m - nb * p.DHW;
       const int cend = min(BN, d.Cout - n0);
-      for (int j = 0; j < cend; ++j) prefetch_l2(p.y + yo + (int64_t)(n0 + j) * d.y_cs);
+      for (int j = 0; j < cend; ++j) {
+        if (EW == 8 && ((j >> 5) & 1) != half) continue;
+        prefetch_l2(p.y + yo + (int64_t)(n0 + j) * d.y_cs);
+      }
       if (ge.mode) {
         for (int j = 0; j < cend; ++j) {
+          if (EW == 8 && ((j >> 5) & 1) != half) continue;
           const int co = n0 + j;
           if (ge.mode == 1 && co < ge.Ch) continue;
           const int c = ge.mode == 2 ? co : co - ge.Ch;
@@ -715,6 +724,7 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
       tc_fence_after();
       for (int cb = 0; cb < BN; cb += 32) {
         if (n0 + cb >= d.Cout) break;
+        if (EW == 8 && ((cb >> 5) & 1) != half) continue;
         uint32_t r0[32], r1[32];
         tmem_ld32(taddr + cb, r0);
         tmem_ld32(taddr + BN + cb, r1);
@@ -1061,12 +1071,13 @@ static int prep_planes(const float* src, int N1, int N2, int C, int Cp, int64_t 
   return 0;
 }
 
-template <int BN, bool PROMOTE, int CG, int OCC = 1>
+template <int BN, bool PROMOTE, int CG, int OCC = 1, int EW = 4>
 static int launch_fwd(const CUtensorMap* m, const FwdP& fp, dim3 grid, cudaStream_t st) {
   using C = Cfg<BN, PROMOTE, CG, OCC>;
+  constexpr int NT = 64 + 32 * EW;
   static bool configured = false;
   if (!configured) {
-    DVD_CUDA(cudaFuncSetAttribute(conv_tma_fwd_kernel<BN, PROMOTE, CG, OCC>,
+    DVD_CUDA(cudaFuncSetAttribute(conv_tma_fwd_kernel<BN, PROMOTE, CG, OCC, EW>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
     configured = true;
   }
@@ -1078,9 +1089,9 @@ static int launch_fwd(const CUtensorMap* m, const FwdP& fp, dim3 grid, cudaStrea
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = cx; attr[0].val.clusterDim.y = cy; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    DVD_CUDA(cudaLaunchKernelEx(&cfg, conv_tma_fwd_kernel<BN, PROMOTE, CG, OCC>, m[0], m[1], m[2], m[3], fp));
+    DVD_CUDA(cudaLaunchKernelEx(&cfg, conv_tma_fwd_kernel<BN, PROMOTE, CG, OCC, EW>, m[0], m[1], m[2], m[3], fp));
   } else {
-    conv_tma_fwd_kernel<BN, PROMOTE, CG, OCC><<<grid, NT, C::SMEM, st>>>(m[0], m[1], m[2], m[3], fp);
+    conv_tma_fwd_kernel<BN, PROMOTE, CG, OCC, EW><<<grid, NT, C::SMEM, st>>>(m[0], m[1], m[2], m[3], fp);
   }
   return 0;
 }
@@ -1310,12 +1321,15 @@ int tma_fwd_launch_ex(ConvP& p, const TmaOperands* ops, const GruEpi* epi, cudaS
   prof_begin(0, 2.0 * p.M * (double)d.Cout * d.Cin * p.taps, st);
   int rc;
   // short reductions on narrow tiles: two CTAs per SM (env DVD_TC_OCC2=0 turns it off)
+  static const bool ew8 = [] { const char* e = getenv("DVD_TC_EW8"); return !(e && e[0] == '0'); }();
   static const bool occ2_on = [] { const char* e = getenv("DVD_TC_OCC2"); return !(e && e[0] == '0'); }();
   const bool occ2 = occ2_on && !promote && !fp.gru.mode && bn <= 128 && p.iters_total <= 40 &&
                     ctas >= 2 * (int64_t)nsm && (pair || bn == 64);     // (one CTA, 128 wide) stages are 64 KB: no room
   if (occ2) {
     if (pair) rc = bn == 128 ? launch_fwd<128, false, 2, 2>(maps, fp, grid, st) : launch_fwd<64, false, 2, 2>(maps, fp, grid, st);
     else rc = launch_fwd<64, false, 1, 2>(maps, fp, grid, st);
+  } else if (pair && ew8 && bn >= 192) {
+    rc = bn == 256 ? launch_fwd<256, false, 2, 1, 8>(maps, fp, grid, st) : launch_fwd<192, false, 2, 1, 8>(maps, fp, grid, st);
   } else if (pair) {
     if (bn == 256) rc = launch_fwd<256, false, 2>(maps, fp, grid, st);
     else if (bn == 192) rc = launch_fwd<192, false, 2>(maps, fp, grid, st);

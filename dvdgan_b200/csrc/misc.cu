@@ -290,7 +290,33 @@ __global__ void channel_sum_kernel(const float* __restrict__ x, int N, int C, in
   if (ne > N) ne = N;
   double s = 0.0;
   const bool vec = (P % 4 == 0) && (n_stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
-  if (P >= blockDim.x) {
+  if (vec && (P >> 2) <= blockDim.x && P >= blockDim.x) {
+    // at most one 128-bit vector per thread and row: fix the column, walk the rows four at a time so that four
+    // independent loads are in flight per thread (one load per loop iteration left this kernel latency-bound)
+    const int P4 = (int)(P >> 2);
+    const int rpp = blockDim.x / P4;
+    const int r = threadIdx.x / P4, q = threadIdx.x - r * P4;
+    if (r < rpp) {
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      const float* base = x + (int64_t)c * P;
+      int n = nb + r;
+      for (; n + 3 * rpp < ne; n += 4 * rpp) {
+        const float4 v0 = __ldg(reinterpret_cast<const float4*>(base + (int64_t)n * n_stride) + q);
+        const float4 v1 = __ldg(reinterpret_cast<const float4*>(base + (int64_t)(n + rpp) * n_stride) + q);
+        const float4 v2 = __ldg(reinterpret_cast<const float4*>(base + (int64_t)(n + 2 * rpp) * n_stride) + q);
+        const float4 v3 = __ldg(reinterpret_cast<const float4*>(base + (int64_t)(n + 3 * rpp) * n_stride) + q);
+        a0 += (v0.x + v0.y) + (v0.z + v0.w);
+        a1 += (v1.x + v1.y) + (v1.z + v1.w);
+        a2 += (v2.x + v2.y) + (v2.z + v2.w);
+        a3 += (v3.x + v3.y) + (v3.z + v3.w);
+      }
+      for (; n < ne; n += rpp) {
+        const float4 v0 = __ldg(reinterpret_cast<const float4*>(base + (int64_t)n * n_stride) + q);
+        a0 += (v0.x + v0.y) + (v0.z + v0.w);
+      }
+      s = ((double)a0 + (double)a1) + ((double)a2 + (double)a3);
+    }
+  } else if (P >= blockDim.x) {
     for (int n = nb; n < ne; ++n) {
       const float* row = x + (int64_t)n * n_stride + (int64_t)c * P;
       float part = 0.f;

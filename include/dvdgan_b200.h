@@ -30,7 +30,7 @@ long long dvd_launch_count(void);
 /* Measurement aid: while enabled, every launch of the dense engines (category 0: dvd_conv_fwd incl. dgrads,
  * 1: dvd_conv_wgrad) is bracketed by CUDA events on its stream.  dvd_prof_read waits for the recorded events,
  * returns the summed device time (ms), algorithmic FLOPs and launch count, and resets the category. */
-int dvd_prof_enable(int on);
+int dvd_prof_enable(int on);   /* 0: off; 1: categories 0 and 1; else a bit mask of categories (0xF = all four) */
 int dvd_prof_read(int category, double* ms, double* flops, long long* launches);
 /* per-shape table of the launches recorded so far (not cleared): "category \t tag \t launches \t ms \t flops-or-bytes";
  * category 2 = operand-plane preparation of the tcgen05 engine (value column = bytes moved) */
