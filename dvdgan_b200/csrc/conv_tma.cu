@@ -1322,14 +1322,18 @@ int tma_fwd_launch_ex(ConvP& p, const TmaOperands* ops, const GruEpi* epi, cudaS
   int rc;
   // short reductions on narrow tiles: two CTAs per SM (env DVD_TC_OCC2=0 turns it off)
   static const bool ew8 = [] { const char* e = getenv("DVD_TC_EW8"); return !(e && e[0] == '0'); }();
+  static const bool ew8b = [] { const char* e = getenv("DVD_TC_EW8B"); return !(e && e[0] == '0'); }();
+  static const int occ2_iters = [] { const char* e = getenv("DVD_TC_OCC2_ITERS"); return e ? atoi(e) : 40; }();
   static const bool occ2_on = [] { const char* e = getenv("DVD_TC_OCC2"); return !(e && e[0] == '0'); }();
-  const bool occ2 = occ2_on && !promote && !fp.gru.mode && bn <= 128 && p.iters_total <= 40 &&
+  const bool occ2 = occ2_on && !promote && !fp.gru.mode && bn <= 128 && p.iters_total <= occ2_iters &&
                     ctas >= 2 * (int64_t)nsm && (pair || bn == 64);     // (one CTA, 128 wide) stages are 64 KB: no room
   if (occ2) {
     if (pair) rc = bn == 128 ? launch_fwd<128, false, 2, 2>(maps, fp, grid, st) : launch_fwd<64, false, 2, 2>(maps, fp, grid, st);
     else rc = launch_fwd<64, false, 1, 2>(maps, fp, grid, st);
   } else if (pair && ew8 && bn >= 192) {
     rc = bn == 256 ? launch_fwd<256, false, 2, 1, 8>(maps, fp, grid, st) : launch_fwd<192, false, 2, 1, 8>(maps, fp, grid, st);
+  } else if (ew8b && !promote && bn == 128) {     // 8 epilogue warps on the 128-wide tiles too (+0.4 %)
+    rc = pair ? launch_fwd<128, false, 2, 1, 8>(maps, fp, grid, st) : launch_fwd<128, false, 1, 1, 8>(maps, fp, grid, st);
   } else if (pair) {
     if (bn == 256) rc = launch_fwd<256, false, 2>(maps, fp, grid, st);
     else if (bn == 192) rc = launch_fwd<192, false, 2>(maps, fp, grid, st);
