@@ -63,6 +63,7 @@ _SIGS = {
     "dvd_scale_residual_bwd": (I, [P, P, P, L, P, P, P, P]),
     "dvd_channel_sum": (I, [P, I, I, L, L, I, P, P, P]),
     "dvd_axpby": (I, [P, F, F, L, P, P]),
+    "dvd_gather_flat": (I, [ctypes.POINTER(c_void_p), ctypes.POINTER(c_int64), ctypes.POINTER(c_int64), I, P, P]),
     "dvd_embedding_fwd": (I, [P, P, I, I, P, P]),
     "dvd_embedding_bwd": (I, [P, P, I, I, P, P]),
     "dvd_dhead_fwd": (I, [P, I, I, I, I, P, P, P, P, P, P, P, P, P]),

@@ -306,13 +306,15 @@ struct Bars {
   __device__ uint64_t* cdrain(int b) const { return base + 2 * STAGES + 3 + b; }
   __device__ uint32_t* slot() const { return reinterpret_cast<uint32_t*>(base + 2 * STAGES + 5); }
   __device__ uint64_t* late() const { return base + 2 * STAGES + 6; }     // "the main loop is about to finish"
-  __device__ void init(uint32_t empty_count = 1, uint32_t drain_count = 128) const {
+  __device__ uint64_t* tfree() const { return base + 2 * STAGES + 7; }    // persistent CTAs: accumulators read out
+  __device__ void init(uint32_t empty_count = 1, uint32_t drain_count = 128, uint32_t tfree_count = 128) const {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(smem_u32(full(s)), 1);
       mbar_init(smem_u32(empty(s)), empty_count);      // one commit per CTA of the cluster that shares the stage
     }
     mbar_init(smem_u32(accum()), 1);
     mbar_init(smem_u32(late()), 1);
+    mbar_init(smem_u32(tfree()), tfree_count);
     for (int b = 0; b < 2; ++b) {
       mbar_init(smem_u32(cfull(b)), 1);
       mbar_init(smem_u32(cdrain(b)), drain_count);
@@ -328,13 +330,12 @@ template <int BN, bool PROMOTE, int STAGES, int STAGE_BYTES, int A_BYTES, int B_
 __device__ __forceinline__ void mma_issue_loop(uint8_t* smem, const Bars<STAGES>& bars, uint32_t tmem_base, int n_iters,
                                                int mn_major, uint32_t lbo, uint32_t sbo, uint32_t kadv,
                                                uint32_t fmt /* 0 = fp16 planes, 1 = bf16 planes */,
-                                               uint16_t commit_mask /* 0: this CTA only */) {
+                                               uint16_t commit_mask /* 0: this CTA only */, int& stage,
+                                               uint32_t& phase /* ring position, carried across tiles */) {
   const uint32_t id_main = make_idesc(BN, mn_major, fmt, fmt, BM * CG);
   const uint32_t id_lo1 = id_main, id_lo2 = id_main;
   const uint32_t lo_col = tmem_base + (PROMOTE ? 2 * BN : BN);
   const int late_it = n_iters > LATE_ITERS ? n_iters - LATE_ITERS : 0;
-  int stage = 0;
-  uint32_t phase = 0;
   for (int it = 0; it < n_iters; ++it) {
     const int chunk = PROMOTE ? it / CHUNK : 0;
     const bool first = PROMOTE ? (it % CHUNK == 0) : (it == 0);
@@ -446,6 +447,7 @@ struct FwdP {
                         // m-tile (each loads 1/cn of its rows), the B tile to the cm CTAs of an n-tile
   GruEpi gru;           // ConvGRU gate / state epilogue (mode 0: plain conv epilogue)
   int prefetch;         // epilogue operands are prefetched into L2 late in the main loop (env DVD_TC_EPI_PREFETCH=0: off)
+  int nt, tiles;        // persistent kernels: n-tiles and total (m-unit, n-tile) tiles
 };
 
 // 32 consecutive channels of one pixel -> fp16 hi / lo planes (same split as prep_planes_kernel, fp16 = 1)
@@ -471,7 +473,10 @@ __device__ __forceinline__ void store_planes32(__half* hi, __half* lo, const flo
 
 // EW = epilogue warps: 4 (one per TMEM lane quarter) or 8 (two per quarter, alternating 32-column chunks) -- the
 // wide tiles hold the only accumulator set of the SM, so the tensor pipe idles until the epilogue is through.
-template <int BN, bool PROMOTE, int CG, int OCC, int EW>
+// PERSIST: one CTA (pair) per SM (pair) walks tiles t = cluster, cluster + #clusters, ... ; the TMA ring keeps running
+// into the next tile while the epilogue drains the accumulators (single TMEM set: the MMAs of the next tile wait for
+// `tfree`), and barrier setup / TMEM allocation / tensor-map fetch are paid once per SM instead of once per tile.
+template <int BN, bool PROMOTE, int CG, int OCC, int EW, bool PERSIST>
 __global__ void __launch_bounds__(64 + 32 * EW, OCC)
 conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                     const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
@@ -494,7 +499,8 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
   const bool leader = CG == 1 || cx == 0;       // pair: rank 0 owns the full barriers and issues the MMAs
 
   static_assert(EW == 4 || (EW == 8 && !PROMOTE), "the promoted accumulator is drained by exactly four warps");
-  if (tid == 0) bars.init(CG == 2 ? 1u : (uint32_t)(cm * cn), CG == 2 ? 256u : 128u);
+  static_assert(!PERSIST || (!PROMOTE && OCC == 1), "persistent tiles use the plain accumulator pair");
+  if (tid == 0) bars.init(CG == 2 ? 1u : (uint32_t)(cm * cn), CG == 2 ? 256u : 128u, (uint32_t)(32 * EW * CG));
   if (warp == 1) {
     if constexpr (CG == 2) {
       asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
@@ -512,14 +518,32 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int m0 = blockIdx.x * BM;
-  const int n0 = blockIdx.y * BN;
   const int it_begin = blockIdx.z * p.iters_per_split;
   const int it_end = min(it_begin + p.iters_per_split, p.iters_total);
   const int n_iters = it_end - it_begin;
+  // tiles of this CTA: persistent = a strided walk over (m-unit, n-tile) with n fastest; otherwise the one tile of
+  // blockIdx.  An m-unit is CG consecutive 128-row tiles (one per CTA of the pair).
+  const int tile_first = PERSIST ? (int)(blockIdx.x / CG) : 0;
+  const int tile_stride = PERSIST ? (int)(gridDim.x / CG) : 1;
+  const int tile_end = PERSIST ? fp.tiles : 1;
+  auto tile_origin = [&](int tile, int* m0, int* n0) {
+    if (PERSIST) {
+      const int nt = tile % fp.nt, mu = tile / fp.nt;
+      *m0 = (mu * CG + (int)(CG == 2 ? cx : 0u)) * BM;
+      *n0 = nt * BN;
+    } else {
+      *m0 = blockIdx.x * BM;
+      *n0 = blockIdx.y * BN;
+    }
+  };
 
   if (warp == 0) {
     if (lane == 0) {
+     int stage = 0;
+     uint32_t phase = 0;
+     for (int tile = tile_first; tile < tile_end; tile += tile_stride) {
+      int m0, n0;
+      tile_origin(tile, &m0, &n0);
       // box origin of this CTA's slice of the A tile: rows [cy * BM/cn, +BM/cn) of the m-tile -> (image, z, y, x);
       // the box covers (bn, bd, bh, bw) = BM/cn rows.  B slice: couts [cx * b_rows, +b_rows) of the n-tile.
       const int a_rows = BM / cn, b_rows = CG == 2 ? BN / 2 : BN / cm;
@@ -536,8 +560,6 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
       const uint16_t mask_b = (uint16_t)(((1u << cm) - 1u) << (cy * cm));     // same n-tile, every m-tile
       int tap = it_begin / p.ck;
       int cchunk = it_begin - tap * p.ck;
-      int stage = 0;
-      uint32_t phase = 0;
       for (int it = 0; it < n_iters; ++it) {
         const int kw = tap % d.kW;
         const int t2 = tap / d.kW;
@@ -577,21 +599,35 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
         if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         if (++cchunk == p.ck) { cchunk = 0; ++tap; }
       }
+     }
     }
     __syncwarp();
   } else if (warp == 1) {
     if (lane == 0 && leader) {
-      // K-major operands: LBO unused (16), SBO = 1024 (8 rows of 128 B), 32 bytes (2 units) per UMMA_K step
-      mma_issue_loop<BN, PROMOTE, C::STAGES, C::STAGE_BYTES, C::A_BYTES, C::B_BYTES, CG>(
-          smem, bars, tmem_base, n_iters, 0, 16, 1024, 2, fp.fp16 ? 0u : 1u,
-          (CG == 1 && clustered) ? (uint16_t)((1u << (cm * cn)) - 1u) : (uint16_t)0);
+      int stage = 0, ti = 0;
+      uint32_t phase = 0;
+      for (int tile = tile_first; tile < tile_end; tile += tile_stride, ++ti) {
+        if (PERSIST && ti > 0) {        // the epilogue warps (of both CTAs of a pair) have read the previous tile out
+          mbar_wait(smem_u32(bars.tfree()), (uint32_t)((ti - 1) & 1));
+          tc_fence_after();
+        }
+        // K-major operands: LBO unused (16), SBO = 1024 (8 rows of 128 B), 32 bytes (2 units) per UMMA_K step
+        mma_issue_loop<BN, PROMOTE, C::STAGES, C::STAGE_BYTES, C::A_BYTES, C::B_BYTES, CG>(
+            smem, bars, tmem_base, n_iters, 0, 16, 1024, 2, fp.fp16 ? 0u : 1u,
+            (CG == 1 && clustered) ? (uint16_t)((1u << (cm * cn)) - 1u) : (uint16_t)0, stage, phase);
+      }
     }
     __syncwarp();
   } else {
-    // ---------------- epilogue: warps 2..(EW+1); a warp may only touch TMEM lanes [32*(warp%4), +32); with EW = 8 the
-    // two warps of a quarter take alternate 32-column chunks
-    const int q = warp & 3;
-    const int half = (warp - 2) >> 2;
+   // ---------------- epilogue: warps 2..(EW+1); a warp may only touch TMEM lanes [32*(warp%4), +32); with EW = 8 the
+   // two warps of a quarter take alternate 32-column chunks
+   const int q = warp & 3;
+   const int half = (warp - 2) >> 2;
+   int ti = 0;
+   for (int tile = tile_first; tile < tile_end; tile += tile_stride, ++ti) {
+    int m0, n0;
+    tile_origin(tile, &m0, &n0);
+    const uint32_t tpar = (uint32_t)(ti & 1);        // phase of the per-tile barriers (accum, late)
     const int row = q * 32 + lane;
     const int m = m0 + row;
     const bool ok = m < p.M;
@@ -693,7 +729,7 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
     };
     // While the main loop runs these warps are idle: pull everything the epilogue will read into L2, so its loads pay
     // an L2 hit instead of a DRAM round trip per 32-channel chunk.
-    if (fp.prefetch && !p.atomic_out && (d.accumulate || ge.mode)) mbar_wait(smem_u32(bars.late()), 0);
+    if (fp.prefetch && !p.atomic_out && (d.accumulate || ge.mode)) mbar_wait(smem_u32(bars.late()), tpar);
     if (fp.prefetch && ok && !p.atomic_out && (d.accumulate || ge.mode)) {
       const int nb = m / p.DHW, pix = m - nb * p.DHW;
       const int cend = min(BN, d.Cout - n0);
@@ -720,7 +756,7 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
         for (int cb = 0; cb < BN; cb += 32) emit32(cb, acc + cb);
       }
     } else {
-      mbar_wait(smem_u32(accum_bar), 0);
+      mbar_wait(smem_u32(accum_bar), tpar);
       tc_fence_after();
       for (int cb = 0; cb < BN; cb += 32) {
         if (n0 + cb >= d.Cout) break;
@@ -737,6 +773,11 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
       }
     }
     tc_fence_before();
+    if (PERSIST) {        // this thread's TMEM reads of the tile are complete: the next tile's MMAs may overwrite it
+      if constexpr (CG == 2) mbar_arrive_cluster(mapa_rank(smem_u32(bars.tfree()), 0));
+      else mbar_arrive(smem_u32(bars.tfree()));
+    }
+   }
   }
 
   __syncthreads();
@@ -897,9 +938,11 @@ conv_tma_wgrad_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_c
     if (lane == 0 && leader) {
       // MN-major operands: LBO = 8192 (next 64-wide MN block), SBO = 1024 (next 8 k-rows); one UMMA_K step =
       // 16 k-rows of 128 B = 2048 B = 128 units.  dY is a gradient, so both operands use bf16 planes.
+      int stage = 0;
+      uint32_t phase = 0;
       mma_issue_loop<BN, PROMOTE, C::STAGES, C::STAGE_BYTES, C::A_BYTES, C::B_BYTES, CG>(
           smem, bars, tmem_base, n_iters, 1, 8192, 1024, 128, 1u,
-          (CG == 1 && clustered) ? (uint16_t)((1u << (cm * cn)) - 1u) : (uint16_t)0);
+          (CG == 1 && clustered) ? (uint16_t)((1u << (cm * cn)) - 1u) : (uint16_t)0, stage, phase);
     }
     __syncwarp();
   } else {
@@ -1071,15 +1114,19 @@ static int prep_planes(const float* src, int N1, int N2, int C, int Cp, int64_t 
   return 0;
 }
 
-template <int BN, bool PROMOTE, int CG, int OCC = 1, int EW = 4>
+template <int BN, bool PROMOTE, int CG, int OCC = 1, int EW = 4, bool PERSIST = false>
 static int launch_fwd(const CUtensorMap* m, const FwdP& fp, dim3 grid, cudaStream_t st) {
   using C = Cfg<BN, PROMOTE, CG, OCC>;
   constexpr int NT = 64 + 32 * EW;
   static bool configured = false;
   if (!configured) {
-    DVD_CUDA(cudaFuncSetAttribute(conv_tma_fwd_kernel<BN, PROMOTE, CG, OCC, EW>,
+    DVD_CUDA(cudaFuncSetAttribute(conv_tma_fwd_kernel<BN, PROMOTE, CG, OCC, EW, PERSIST>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
     configured = true;
+  }
+  if (PERSIST) {          // one CTA (pair) per SM (pair), or fewer when there are fewer tiles
+    const int slots = num_sms() / CG;
+    grid = dim3((unsigned)(CG * std::min(fp.tiles, slots)), 1, 1);
   }
   const int cx = CG == 2 ? 2 : fp.cm, cy = CG == 2 ? 1 : fp.cn;
   if (cx * cy > 1) {
@@ -1089,9 +1136,9 @@ static int launch_fwd(const CUtensorMap* m, const FwdP& fp, dim3 grid, cudaStrea
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = cx; attr[0].val.clusterDim.y = cy; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    DVD_CUDA(cudaLaunchKernelEx(&cfg, conv_tma_fwd_kernel<BN, PROMOTE, CG, OCC, EW>, m[0], m[1], m[2], m[3], fp));
+    DVD_CUDA(cudaLaunchKernelEx(&cfg, conv_tma_fwd_kernel<BN, PROMOTE, CG, OCC, EW, PERSIST>, m[0], m[1], m[2], m[3], fp));
   } else {
-    conv_tma_fwd_kernel<BN, PROMOTE, CG, OCC, EW><<<grid, NT, C::SMEM, st>>>(m[0], m[1], m[2], m[3], fp);
+    conv_tma_fwd_kernel<BN, PROMOTE, CG, OCC, EW, PERSIST><<<grid, NT, C::SMEM, st>>>(m[0], m[1], m[2], m[3], fp);
   }
   return 0;
 }
@@ -1321,6 +1368,12 @@ int tma_fwd_launch_ex(ConvP& p, const TmaOperands* ops, const GruEpi* epi, cudaS
   prof_begin(0, 2.0 * p.M * (double)d.Cout * d.Cin * p.taps, st);
   int rc;
   // short reductions on narrow tiles: two CTAs per SM (env DVD_TC_OCC2=0 turns it off)
+  // persistent CTA pairs when there is more than one wave of tiles (env DVD_TC_PERSIST=0 turns it off)
+  static const bool persist_on = [] { const char* e = getenv("DVD_TC_PERSIST"); return !(e && e[0] == '0'); }();
+  fp.nt = ceil_div(d.Cout, bn);
+  fp.tiles = (mt / (pair ? 2 : 1)) * fp.nt;
+  const bool persist = persist_on && pair && !promote && nsplit == 1 && fp.cm * fp.cn == 1 &&
+                       fp.tiles > nsm / 2;
   static const bool ew8 = [] { const char* e = getenv("DVD_TC_EW8"); return !(e && e[0] == '0'); }();
   static const bool ew8b = [] { const char* e = getenv("DVD_TC_EW8B"); return !(e && e[0] == '0'); }();
   static const int occ2_iters = [] { const char* e = getenv("DVD_TC_OCC2_ITERS"); return e ? atoi(e) : 40; }();
@@ -1330,6 +1383,10 @@ int tma_fwd_launch_ex(ConvP& p, const TmaOperands* ops, const GruEpi* epi, cudaS
   if (occ2) {
     if (pair) rc = bn == 128 ? launch_fwd<128, false, 2, 2>(maps, fp, grid, st) : launch_fwd<64, false, 2, 2>(maps, fp, grid, st);
     else rc = launch_fwd<64, false, 1, 2>(maps, fp, grid, st);
+  } else if (persist && pair && bn >= 128) {      // persistent CTA pairs, 8 epilogue warps
+    if (bn == 256) rc = launch_fwd<256, false, 2, 1, 8, true>(maps, fp, grid, st);
+    else if (bn == 192) rc = launch_fwd<192, false, 2, 1, 8, true>(maps, fp, grid, st);
+    else rc = launch_fwd<128, false, 2, 1, 8, true>(maps, fp, grid, st);
   } else if (pair && ew8 && bn >= 192) {
     rc = bn == 256 ? launch_fwd<256, false, 2, 1, 8>(maps, fp, grid, st) : launch_fwd<192, false, 2, 1, 8>(maps, fp, grid, st);
   } else if (ew8b && !promote && bn == 128) {     // 8 epilogue warps on the 128-wide tiles too (+0.4 %)

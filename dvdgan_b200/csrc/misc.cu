@@ -346,6 +346,22 @@ __global__ void channel_sum_kernel(const float* __restrict__ x, int N, int C, in
   s = block_sum(s, red);
   if (threadIdx.x == 0) atomicAdd(acc + c, s);
 }
+// copy (or zero-fill, src == nullptr) up to kMax tensors into their slices of a flat arena in ONE launch
+struct GatherP {
+  static constexpr int kMax = 96;
+  const float* src[kMax];
+  int64_t off[kMax];
+  int64_t cnt[kMax];
+  int n;
+};
+__global__ void gather_flat_kernel(const GatherP gp, float* __restrict__ flat) {
+  const int t = blockIdx.y;
+  const float* __restrict__ src = gp.src[t];
+  float* dst = flat + gp.off[t];
+  const int64_t n = gp.cnt[t];
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    dst[i] = src ? __ldg(src + i) : 0.f;
+}
 __global__ void axpby_kernel(const float* __restrict__ x, float a, float b, int64_t n, float* __restrict__ y) {
   GRID_STRIDE(i, n) y[i] = b == 0.f ? a * __ldg(x + i) : fmaf(a, __ldg(x + i), b * y[i]);
 }
@@ -617,6 +633,29 @@ extern "C" int dvd_channel_sum(const float* x, int N, int C, int64_t P, int64_t 
   DVD_LAUNCH_CHECK();
   double_to_float_kernel<<<ceil_div(C, 128), 128, 0, st>>>(acc, C, accumulate, out);
   DVD_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int dvd_gather_flat(const float* const* srcs, const int64_t* offs, const int64_t* counts, int n, float* flat,
+                               void* stream) {
+  dvd::ProfScope _ps(3, "gather_flat", dvd::as_stream(stream));
+  DVD_CHECK_ARG(srcs && offs && counts && flat && n >= 0);
+  cudaStream_t st = as_stream(stream);
+  for (int i0 = 0; i0 < n; i0 += GatherP::kMax) {
+    GatherP gp;
+    gp.n = n - i0 < GatherP::kMax ? n - i0 : GatherP::kMax;
+    int64_t longest = 1;
+    for (int i = 0; i < gp.n; ++i) {
+      DVD_CHECK_ARG(counts[i0 + i] >= 0 && offs[i0 + i] >= 0);
+      gp.src[i] = srcs[i0 + i];
+      gp.off[i] = offs[i0 + i];
+      gp.cnt[i] = counts[i0 + i];
+      if (gp.cnt[i] > longest) longest = gp.cnt[i];
+    }
+    int bx = (int)ceil_div<int64_t>(longest, 256 * 8);
+    if (bx > 2 * num_sms()) bx = 2 * num_sms();
+    gather_flat_kernel<<<dim3(bx, gp.n), 256, 0, st>>>(gp, flat);
+    DVD_LAUNCH_CHECK();
+  }
   return 0;
 }
 extern "C" int dvd_axpby(const float* x, float a, float b, int64_t n, float* y, void* stream) {

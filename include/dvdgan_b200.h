@@ -197,6 +197,10 @@ int dvd_channel_sum(const float* x, int N, int C, int64_t P, int64_t n_stride, i
                     void* scratch, void* stream);
 /* axpby: y = a*x + b*y */
 int dvd_axpby(const float* x, float a, float b, int64_t n, float* y, void* stream);
+/* Multi-tensor gather of the flat-arena optimizer (trainer.py:136-141 keeps one gradient tensor per parameter):
+ * flat[offs[i] .. offs[i]+counts[i]) = srcs[i][0 .. counts[i])  (zeros when srcs[i] == NULL), i < n, in ceil(n/96)
+ * launches.  srcs / offs / counts are HOST arrays of device pointers / element offsets / element counts. */
+int dvd_gather_flat(const float* const* srcs, const int64_t* offs, const int64_t* counts, int n, float* flat, void* stream);
 /* Embedding rows (Generator.py:70): y[i] = w[idx[i]]; bwd: dw[idx[i]] += dy[i] (dw pre-zeroed by caller). */
 int dvd_embedding_fwd(const float* w, const int64_t* idx, int n, int dim, float* y, void* stream);
 int dvd_embedding_bwd(const float* dy, const int64_t* idx, int n, int dim, float* dw, void* stream);

@@ -1,5 +1,5 @@
 """world_size-2 gloo test of the data-parallel host logic: batch sharding and the flat-arena
-gradient all-reduce + Adam.  The two CUDA kernels FlatAdam calls (copy into the arena, fused Adam) are replaced
+gradient all-reduce + Adam.  The two CUDA kernels FlatAdam calls (multi-tensor gather into the arena, fused Adam) are replaced
 by torch-CPU stand-ins HERE ONLY, so that the collective / averaging logic runs without a GPU; the kernels
 themselves are covered by the -m gpu tests."""
 import os
@@ -13,8 +13,16 @@ import torch.multiprocessing as mp
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _cpu_copy(src, flat, off, k):
-    flat[off:off + k].copy_(src.reshape(-1))
+def _cpu_gather(srcs, offs, cnts, n, flat):
+    """host stand-in for dvd_gather_flat: same (pointer, offset, count) table, plain memmove / memset"""
+    import ctypes
+    base = flat.data_ptr()
+    for i in range(n):
+        dst = base + 4 * offs[i]
+        if srcs[i] is None:
+            ctypes.memset(dst, 0, 4 * cnts[i])
+        else:
+            ctypes.memmove(dst, srcs[i], 4 * cnts[i])
 
 
 def _cpu_adam(p, g, m, v, lr, b1, b2, eps, t, scale):
@@ -31,7 +39,7 @@ def _worker(rank, world, port, q):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from dvdgan_b200.trainer import FlatAdam, shard_batch
-    FlatAdam._copy = staticmethod(_cpu_copy)
+    FlatAdam._gather = staticmethod(_cpu_gather)
     FlatAdam._adam = staticmethod(_cpu_adam)
     torch.manual_seed(0)                       # identical replicas
     net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 1))
