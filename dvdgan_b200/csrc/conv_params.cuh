@@ -32,6 +32,11 @@ struct TmaOperands {
   const void* w_hi = nullptr;     // nullptr: split p.w inside the call
   const void* w_lo = nullptr;
   int CoutP = 0;                  // rows per tap of the weight planes
+  // a_hi / a_lo may be a window of larger shared planes: channels [a_c_off, a_c_off + Cin) of pixels that hold a_Cp
+  // channels each, image n at element offset n * a_img_stride from a_hi (0 / 0 / 0: dense [N][D*H*W][round64(Cin)])
+  int a_Cp = 0;
+  int a_c_off = 0;
+  int64_t a_img_stride = 0;
 };
 // ConvGRU epilogues (ConvGRU.py:47-52) applied to v = accumulator + y (y holds the x-half pre-activations):
 //  mode 1 (h-half of update|reset, Cout = 2*Ch): co <  Ch: y = u = sigmoid(v)

@@ -448,6 +448,7 @@ struct FwdP {
   GruEpi gru;           // ConvGRU gate / state epilogue (mode 0: plain conv epilogue)
   int prefetch;         // epilogue operands are prefetched into L2 late in the main loop (env DVD_TC_EPI_PREFETCH=0: off)
   int nt, tiles;        // persistent kernels: n-tiles and total (m-unit, n-tile) tiles
+  int a_c_off;          // first channel of the A operand inside (shared) planes
 };
 
 // 32 consecutive channels of one pixel -> fp16 hi / lo planes (same split as prep_planes_kernel, fp16 = 1)
@@ -568,25 +569,26 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
         mbar_wait(smem_u32(empty_bar + stage), phase ^ 1);
         const uint32_t fb = smem_u32(full_bar + stage);
         const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
-        const int c0 = cchunk * BKC;
+        const int c0 = cchunk * BKC;                 // channel block of the weights; the activations may be offset
+        const int ca = c0 + fp.a_c_off;
         const int px = x0 + kw - d.kW / 2, py = y0 + kh - d.kH / 2, pz = z0 + kd - d.kD / 2;
         const int brow = tap * fp.CoutP + n0 + (int)cx * b_rows;
         if constexpr (CG == 2) {
           // both CTAs' bytes are counted on rank 0's barrier
           if (leader) mbar_expect_tx(fb, 2 * C::STAGE_BYTES);
           const uint32_t fbl = mapa_rank(fb, 0);
-          tma_load_5d_pair(sa, &tmA_hi, fbl, c0, px, py, pz, img);
-          tma_load_5d_pair(sa + C::A_BYTES, &tmA_lo, fbl, c0, px, py, pz, img);
+          tma_load_5d_pair(sa, &tmA_hi, fbl, ca, px, py, pz, img);
+          tma_load_5d_pair(sa + C::A_BYTES, &tmA_lo, fbl, ca, px, py, pz, img);
           tma_load_2d_pair(sa + 2 * C::A_BYTES, &tmB_hi, fbl, c0, brow);
           tma_load_2d_pair(sa + 2 * C::A_BYTES + C::B_BYTES, &tmB_lo, fbl, c0, brow);
         } else {
           mbar_expect_tx(fb, C::STAGE_BYTES);
           if (cn > 1) {
-            tma_load_5d_mc(sa + a_off, &tmA_hi, fb, mask_a, c0, px, py, pz, img);
-            tma_load_5d_mc(sa + C::A_BYTES + a_off, &tmA_lo, fb, mask_a, c0, px, py, pz, img);
+            tma_load_5d_mc(sa + a_off, &tmA_hi, fb, mask_a, ca, px, py, pz, img);
+            tma_load_5d_mc(sa + C::A_BYTES + a_off, &tmA_lo, fb, mask_a, ca, px, py, pz, img);
           } else {
-            tma_load_5d(sa, &tmA_hi, fb, c0, px, py, pz, img);
-            tma_load_5d(sa + C::A_BYTES, &tmA_lo, fb, c0, px, py, pz, img);
+            tma_load_5d(sa, &tmA_hi, fb, ca, px, py, pz, img);
+            tma_load_5d(sa + C::A_BYTES, &tmA_lo, fb, ca, px, py, pz, img);
           }
           if (cm > 1) {
             tma_load_2d_mc(sa + 2 * C::A_BYTES + b_off, &tmB_hi, fb, mask_b, c0, brow);
@@ -1015,12 +1017,13 @@ static EncodeFn get_encode() {
 }
 
 // channels-last planes [N][D][H][W][Cp] -> 5-D map (c, w, h, d, n), box (64, bw, bh, bd, bn), 128B swizzle
-static int make_act_map(CUtensorMap* tm, const void* base, int N, int D, int H, int W, int Cp, const TileGeom& g) {
+static int make_act_map(CUtensorMap* tm, const void* base, int N, int D, int H, int W, int Cp, const TileGeom& g,
+                        int64_t img_stride_elems = 0) {
   EncodeFn enc = get_encode();
   if (!enc) return fail("cuTensorMapEncodeTiled unavailable%s (%s:%d)", "", __FILE__, __LINE__);
   cuuint64_t gdim[5] = {(cuuint64_t)Cp, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
   cuuint64_t gstr[4] = {(cuuint64_t)Cp * 2, (cuuint64_t)W * Cp * 2, (cuuint64_t)H * W * Cp * 2,
-                        (cuuint64_t)D * H * W * Cp * 2};
+                        img_stride_elems ? (cuuint64_t)img_stride_elems * 2 : (cuuint64_t)D * H * W * Cp * 2};
   cuuint32_t box[5] = {64, (cuuint32_t)g.bw, (cuuint32_t)g.bh, (cuuint32_t)g.bd, (cuuint32_t)g.bn};
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), gdim, gstr, box, estr,
@@ -1357,8 +1360,12 @@ int tma_fwd_launch_ex(ConvP& p, const TmaOperands* ops, const GruEpi* epi, cudaS
   TileGeom ga = fp.g;
   while (fp.cn > 1 && !tile_geom(BM / fp.cn, N, d.D, d.H, d.W, &ga)) fp.cn >>= 1;
   if (fp.cn == 1) ga = fp.g;
-  DVD_TRY(make_act_map(&maps[0], a_hi, N, d.D, d.H, d.W, CinP, ga));
-  DVD_TRY(make_act_map(&maps[1], a_lo, N, d.D, d.H, d.W, CinP, ga));
+  const int a_Cp = (ext_a && ops->a_Cp) ? ops->a_Cp : CinP;
+  const int64_t a_stride = ext_a ? ops->a_img_stride : 0;
+  fp.a_c_off = ext_a ? ops->a_c_off : 0;
+  if (ext_a) DVD_CHECK_ARG(a_Cp % 64 == 0 && fp.a_c_off % 64 == 0 && fp.a_c_off + CinP <= a_Cp);
+  DVD_TRY(make_act_map(&maps[0], a_hi, N, d.D, d.H, d.W, a_Cp, ga, a_stride));
+  DVD_TRY(make_act_map(&maps[1], a_lo, N, d.D, d.H, d.W, a_Cp, ga, a_stride));
   DVD_TRY(make_w_map(&maps[2], w_hi, p.taps * CoutP, CinP, pair ? bn / 2 : bn / fp.cm));
   DVD_TRY(make_w_map(&maps[3], w_lo, p.taps * CoutP, CinP, pair ? bn / 2 : bn / fp.cm));
   fp.c = p;

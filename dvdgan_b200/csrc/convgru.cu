@@ -5,6 +5,7 @@
 // (B,T,3Ch,H,W) buffer = (update, reset, out) that is activated in place and, in the backward sweep,
 // overwritten in place with the pre-activation gradients, which then feed ONE batched x-dgrad and the batched
 // weight gradients.
+#include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
 #include "common.cuh"
@@ -83,6 +84,120 @@ __global__ void gru_bwd2_kernel(float* __restrict__ g_t, int64_t g_bs, const flo
     const float drh = d_rh[i];
     carry_out[i] += drh * rr;
     g[chw + r] = drh * h * rr * (1.f - rr);
+  }
+}
+
+// ---- backward kernels that ALSO write the bf16 (hi, lo * 2^8) operand planes of the pre-activation gradients.
+// Planes: [B*T][HW][G3P] channels-last, channel order (da_u | da_r | da_o) = the layer's gate order; they are read
+// by the two per-step dgrad GEMMs, the batched x-dgrad and the three weight-gradient GEMMs, so the gradients are
+// split exactly once, by the kernel that produces them.  Block = 32 pixels x 64 channels of one image, transposed
+// through shared memory (NCHW-coalesced loads and fp32 stores, channels-last 128-bit plane stores).
+__device__ __forceinline__ void bf16_split8(const float* v, uint4* hi, uint4* lo) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __nv_bfloat162 hp = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    const float2 hf = __bfloat1622float2(hp);
+    const __nv_bfloat162 lp = __floats2bfloat162_rn((v[2 * i] - hf.x) * 256.f, (v[2 * i + 1] - hf.y) * 256.f);
+    h[i] = *reinterpret_cast<const uint32_t*>(&hp);
+    l[i] = *reinterpret_cast<const uint32_t*>(&lp);
+  }
+  *hi = make_uint4(h[0], h[1], h[2], h[3]);
+  *lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+// part 1 (see gru_bwd1_kernel) for image b = blockIdx.z, channels [64*blockIdx.y, +64), pixels [32*blockIdx.x, +32)
+__global__ void __launch_bounds__(256) gru_bwd1_planes_kernel(
+    float* __restrict__ g_t, int64_t g_bs, const float* __restrict__ hp, int64_t hp_bs, const float* __restrict__ dh_t,
+    int64_t dh_bs, const float* __restrict__ carry_in, float* __restrict__ carry_out, int Ch, int HW,
+    __nv_bfloat16* __restrict__ pl_hi, __nv_bfloat16* __restrict__ pl_lo, int64_t pl_img_stride, int G3P) {
+  __shared__ float t_o[64][33], t_u[64][33];
+  const int b = blockIdx.z, c0 = blockIdx.y * 64, pix0 = blockIdx.x * 32, tid = threadIdx.x;
+  const int64_t chw = (int64_t)Ch * HW;
+  {
+    const int px = tid & 31, pix = pix0 + px;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int cl = (tid >> 5) + 8 * j, c = c0 + cl;
+      float da_o = 0.f, da_u = 0.f;
+      if (pix < HW) {
+        const int64_t r = (int64_t)c * HW + pix;
+        float* g = g_t + b * g_bs;
+        const float u = g[r], o = g[2 * chw + r];
+        const float h = hp ? hp[b * hp_bs + r] : 0.f;
+        float dhn = dh_t[b * dh_bs + r];
+        if (carry_in) dhn += carry_in[b * chw + r];
+        da_o = dhn * u * (1.f - o * o);
+        da_u = dhn * (o - h) * u * (1.f - u);
+        g[2 * chw + r] = da_o;
+        g[r] = da_u;
+        carry_out[b * chw + r] = dhn * (1.f - u);
+      }
+      t_o[cl][px] = da_o;
+      t_u[cl][px] = da_u;
+    }
+  }
+  __syncthreads();
+  {
+    const int px = tid >> 3, q = tid & 7, pix = pix0 + px;
+    if (pix < HW) {
+      float vo[8], vu[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { vo[i] = t_o[q * 8 + i][px]; vu[i] = t_u[q * 8 + i][px]; }
+      const int64_t row = (int64_t)b * pl_img_stride + (int64_t)pix * G3P + c0 + q * 8;
+      uint4 hi, lo;
+      bf16_split8(vu, &hi, &lo);
+      *reinterpret_cast<uint4*>(pl_hi + row) = hi;
+      *reinterpret_cast<uint4*>(pl_lo + row) = lo;
+      bf16_split8(vo, &hi, &lo);
+      *reinterpret_cast<uint4*>(pl_hi + row + 2 * Ch) = hi;
+      *reinterpret_cast<uint4*>(pl_lo + row + 2 * Ch) = lo;
+    }
+  }
+}
+
+// part 2 (see gru_bwd2_kernel): da_r -> reset slot and the planes at channel offset Ch
+__global__ void __launch_bounds__(256) gru_bwd2_planes_kernel(
+    float* __restrict__ g_t, int64_t g_bs, const float* __restrict__ hp, int64_t hp_bs, const float* __restrict__ d_rh,
+    float* __restrict__ carry_out, int Ch, int HW, __nv_bfloat16* __restrict__ pl_hi, __nv_bfloat16* __restrict__ pl_lo,
+    int64_t pl_img_stride, int G3P) {
+  __shared__ float t_r[64][33];
+  const int b = blockIdx.z, c0 = blockIdx.y * 64, pix0 = blockIdx.x * 32, tid = threadIdx.x;
+  const int64_t chw = (int64_t)Ch * HW;
+  {
+    const int px = tid & 31, pix = pix0 + px;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int cl = (tid >> 5) + 8 * j, c = c0 + cl;
+      float da_r = 0.f;
+      if (pix < HW) {
+        const int64_t r = (int64_t)c * HW + pix;
+        float* g = g_t + b * g_bs;
+        if (hp) {
+          const float rr = g[chw + r];
+          const float h = hp[b * hp_bs + r];
+          const float drh = d_rh[b * chw + r];
+          carry_out[b * chw + r] += drh * rr;
+          da_r = drh * h * rr * (1.f - rr);
+        }
+        g[chw + r] = da_r;
+      }
+      t_r[cl][px] = da_r;
+    }
+  }
+  __syncthreads();
+  {
+    const int px = tid >> 3, q = tid & 7, pix = pix0 + px;
+    if (pix < HW) {
+      float v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = t_r[q * 8 + i][px];
+      const int64_t row = (int64_t)b * pl_img_stride + (int64_t)pix * G3P + Ch + c0 + q * 8;
+      uint4 hi, lo;
+      bf16_split8(v, &hi, &lo);
+      *reinterpret_cast<uint4*>(pl_hi + row) = hi;
+      *reinterpret_cast<uint4*>(pl_lo + row) = lo;
+    }
   }
 }
 
@@ -293,36 +408,6 @@ extern "C" int dvd_convgru_layer_bwd(const float* x, int64_t x_bs, int64_t x_ts,
     DVD_TRY(tma_split_weights(ws.whoT, taps, Ch, Ch, ChP, 0, ws.whoT_hi, ws.whoT_lo, st));
     DVD_TRY(tma_split_weights(ws.whurT, taps, 2 * Ch, Ch, ChP, 0, ws.whurT_hi, ws.whurT_lo, st));
   }
-  for (int t = T - 1; t >= 0; --t) {
-    const float* hp = t > 0 ? h + (int64_t)(t - 1) * h_ts : h0;
-    const int64_t hp_bs = t > 0 ? h_bs : chw;
-    float* g_t = gates + (int64_t)t * g_ts;
-    { ProfScope ps(3, "gru_bwd1", st); gru_bwd1_kernel<<<eb, 256, 0, st>>>(g_t, g_bs, hp, hp_bs, dh + (int64_t)t * h_ts, h_bs, carry_in, carry_out, B, chw); }
-    DVD_LAUNCH_CHECK();
-    if (hp) {                                                 // d(rh) = conv_o^T(da_o), h-half
-      if (wplanes) {
-        TmaOperands op;
-        op.w_hi = ws.whoT_hi; op.w_lo = ws.whoT_lo; op.CoutP = ChP;
-        DVD_TRY(conv_fwd_ex(&d_rh, g_t + 2 * chw, ws.whoT, ws.d_rh, &op, nullptr, st));
-      } else {
-        DVD_TRY(dvd_conv_fwd(&d_rh, g_t + 2 * chw, ws.whoT, nullptr, nullptr, ws.d_rh, stream));
-      }
-    }
-    { ProfScope ps(3, "gru_bwd2", st); gru_bwd2_kernel<<<eb, 256, 0, st>>>(g_t, g_bs, hp, hp_bs, ws.d_rh, carry_out, B, chw); }
-    DVD_LAUNCH_CHECK();
-    if (hp) {                                                 // dh_prev += conv_u^T(da_u) + conv_r^T(da_r)
-      if (wplanes) {
-        TmaOperands op;
-        op.w_hi = ws.whurT_hi; op.w_lo = ws.whurT_lo; op.CoutP = ChP;
-        DVD_TRY(conv_fwd_ex(&d_hp, g_t, ws.whurT, carry_out, &op, nullptr, st));
-      } else {
-        DVD_TRY(dvd_conv_fwd(&d_hp, g_t, ws.whurT, nullptr, nullptr, carry_out, stream));
-      }
-    }
-    carry_in = carry_out;
-    carry_out = (carry_out == ws.carry0) ? ws.carry1 : ws.carry0;
-  }
-  if (dh0) DVD_CUDA(cudaMemcpyAsync(dh0, carry_in, sizeof(float) * (size_t)B * chw, cudaMemcpyDeviceToDevice, st));
   // The pre-activation gradients (da_u | da_r | da_o) of all frames feed four GEMMs (x-dgrad and the three weight
   // gradients): split them into bf16 planes ONCE and hand the planes to all four (channel / frame offsets in the
   // TMA coordinates) instead of re-splitting the largest tensor of the layer per GEMM.
@@ -345,13 +430,76 @@ extern "C" int dvd_convgru_layer_bwd(const float* x, int64_t x_bs, int64_t x_ts,
     share = conv_wgrad_ex_eligible(&d_wx, &yo);
     yo.y_hi = nullptr;
   }
+  // gplanes: the BPTT kernels write the planes themselves (frame by frame) and the per-step dgrad GEMMs read their
+  // A operand from them too; otherwise the planes are split from the fp32 buffer after the sweep
+  static const bool gplanes_on = [] { const char* e = getenv("DVD_GRU_BWD_PLANES"); return !(e && e[0] == '0'); }();
+  const bool gplanes = gplanes_on && share && wplanes && Ch % 64 == 0;
+  __nv_bfloat16 *pl_hi = nullptr, *pl_lo = nullptr;
+  const int64_t pl_frame = (int64_t)HW * G3P, pl_img = (int64_t)T * pl_frame;
   if (share) {
     const size_t elems = (size_t)B * T * HW * G3P;
     DVD_TRY(tma_scratch_alloc(&gp.p, 2 * elems * sizeof(uint16_t) + 256, st));
     yo.y_hi = gp.p;
     yo.y_lo = reinterpret_cast<uint16_t*>(gp.p) + elems;
-    DVD_TRY(tma_split_gradients(gates, B * T, 3 * Ch, g_ts, HW, HW, const_cast<void*>(yo.y_hi), const_cast<void*>(yo.y_lo), st));
+    pl_hi = reinterpret_cast<__nv_bfloat16*>(gp.p);
+    pl_lo = pl_hi + elems;
   }
+  for (int t = T - 1; t >= 0; --t) {
+    const float* hp = t > 0 ? h + (int64_t)(t - 1) * h_ts : h0;
+    const int64_t hp_bs = t > 0 ? h_bs : chw;
+    float* g_t = gates + (int64_t)t * g_ts;
+    const dim3 pgrid(ceil_div(HW, 32), Ch / 64, B);
+    if (gplanes) {
+      ProfScope ps(3, "gru_bwd1", st);
+      gru_bwd1_planes_kernel<<<pgrid, 256, 0, st>>>(g_t, g_bs, hp, hp_bs, dh + (int64_t)t * h_ts, h_bs, carry_in,
+                                                     carry_out, Ch, HW, pl_hi + t * pl_frame, pl_lo + t * pl_frame,
+                                                     pl_img, G3P);
+    } else {
+      ProfScope ps(3, "gru_bwd1", st);
+      gru_bwd1_kernel<<<eb, 256, 0, st>>>(g_t, g_bs, hp, hp_bs, dh + (int64_t)t * h_ts, h_bs, carry_in, carry_out, B, chw);
+    }
+    DVD_LAUNCH_CHECK();
+    if (hp) {                                                 // d(rh) = conv_o^T(da_o), h-half
+      if (wplanes) {
+        TmaOperands op;
+        op.w_hi = ws.whoT_hi; op.w_lo = ws.whoT_lo; op.CoutP = ChP;
+        if (gplanes) {
+          op.a_hi = pl_hi + t * pl_frame; op.a_lo = pl_lo + t * pl_frame;
+          op.a_Cp = G3P; op.a_c_off = 2 * Ch; op.a_img_stride = pl_img;
+        }
+        DVD_TRY(conv_fwd_ex(&d_rh, g_t + 2 * chw, ws.whoT, ws.d_rh, &op, nullptr, st));
+      } else {
+        DVD_TRY(dvd_conv_fwd(&d_rh, g_t + 2 * chw, ws.whoT, nullptr, nullptr, ws.d_rh, stream));
+      }
+    }
+    if (gplanes) {
+      ProfScope ps(3, "gru_bwd2", st);
+      gru_bwd2_planes_kernel<<<pgrid, 256, 0, st>>>(g_t, g_bs, hp, hp_bs, ws.d_rh, carry_out, Ch, HW,
+                                                     pl_hi + t * pl_frame, pl_lo + t * pl_frame, pl_img, G3P);
+    } else {
+      ProfScope ps(3, "gru_bwd2", st);
+      gru_bwd2_kernel<<<eb, 256, 0, st>>>(g_t, g_bs, hp, hp_bs, ws.d_rh, carry_out, B, chw);
+    }
+    DVD_LAUNCH_CHECK();
+    if (hp) {                                                 // dh_prev += conv_u^T(da_u) + conv_r^T(da_r)
+      if (wplanes) {
+        TmaOperands op;
+        op.w_hi = ws.whurT_hi; op.w_lo = ws.whurT_lo; op.CoutP = ChP;
+        if (gplanes) {
+          op.a_hi = pl_hi + t * pl_frame; op.a_lo = pl_lo + t * pl_frame;
+          op.a_Cp = G3P; op.a_c_off = 0; op.a_img_stride = pl_img;
+        }
+        DVD_TRY(conv_fwd_ex(&d_hp, g_t, ws.whurT, carry_out, &op, nullptr, st));
+      } else {
+        DVD_TRY(dvd_conv_fwd(&d_hp, g_t, ws.whurT, nullptr, nullptr, carry_out, stream));
+      }
+    }
+    carry_in = carry_out;
+    carry_out = (carry_out == ws.carry0) ? ws.carry1 : ws.carry0;
+  }
+  if (dh0) DVD_CUDA(cudaMemcpyAsync(dh0, carry_in, sizeof(float) * (size_t)B * chw, cudaMemcpyDeviceToDevice, st));
+  if (share && !gplanes)
+    DVD_TRY(tma_split_gradients(gates, B * T, 3 * Ch, g_ts, HW, HW, const_cast<void*>(yo.y_hi), const_cast<void*>(yo.y_lo), st));
   // dx for all frames: one implicit GEMM over the (da_u | da_r | da_o) buffer
   if (share) {
     TmaOperands op;
