@@ -34,10 +34,10 @@ STEP_TFLOP_PER_CLIP = 8.187     # 3*G_fwd + 9*(Ds_fwd 
 STEP_HBM_GB_PER_CLIP = 4.42     # SURVEY.md 8(d), compulsory traffic under ideal fusion, fwd+bwd
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel from the committed `ncu --set full`
 # capture (profiles/): the per-timestep h-half update|reset GEMM of the 32x32 ConvGRU stage, B = 64
-NCU_TRAFFIC_BYTES = 243.9e6
-NCU_TRAFFIC_OF = ("conv_tma_fwd_kernel<256,0,2,1>, M=65536 Cin=256 Cout=512 5x5: dram 149.7 MB read + 94.2 MB write per "
-                  "launch vs 214 MB algorithmic (67 MB operand planes + 13 MB weight planes + 134 MB fp32 output); "
-                  "profiles/r1/README.md")
+NCU_TRAFFIC_BYTES = 173.7e6
+NCU_TRAFFIC_OF = ("conv_tma_fwd_kernel<256,0,2,1,8,1> (persistent CTA pairs), M=65536 Cin=256 Cout=512 5x5: dram 81.7 MB read + "
+                  "92.0 MB write per launch vs 214 MB algorithmic (67 MB operand planes, mostly still in L2 from the split "
+                  "kernel, + 13 MB weight planes + 134 MB fp32 output); profiles/r1/README.md")
 
 
 def parse():
