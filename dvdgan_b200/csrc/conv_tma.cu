@@ -8,18 +8,23 @@
 // bf16's exponent range: hi = bf16(x), lo = bf16((x - hi) * 2^8), x to 2^-17.  (A and B of one tcgen05.mma must
 // share a format: mixed fp16/bf16 descriptors raise an illegal-instruction fault.)  The GEMM issues
 //   D_main += A_hi*B_hi ,   D_lo += A_lo*B_hi + A_hi*B_lo          (result = D_main + D_lo / s)
-// into separate fp32 TMEM accumulators.  The tensor core truncates its accumulator on every add (measured: error
-// grows linearly with K), so (a) the many small cross terms are kept out of the large accumulator and (b) with
-// PROMOTE the main accumulator ping-pongs between two TMEM regions in chunks of 8 k-blocks; the epilogue warps
-// drain each finished chunk into fp32 registers (round-to-nearest adds) while the next chunk is being issued.
+// into separate fp32 TMEM accumulators (the many small cross terms stay out of the large accumulator).  The tensor core
+// truncates its accumulator on every add (measured: a bias of ~K/16 * 2^-25 relative, 1.4e-5 at K = 12800); the optional
+// PROMOTE mode (env DVD_TC_PROMOTE, off by default, <= 128-column tiles only) ping-pongs the main accumulator between two
+// TMEM regions in chunks of 8 k-blocks and drains each finished chunk into fp32 registers.
 //
-// forward CTA (192 threads): warp 0 = TMA producer (one lane), warp 1 = TMEM alloc + tcgen05.mma issuer (one lane),
-// warps 2-5 = epilogue.  A tile = 128 output pixels x 64 channels, fetched per tap as ONE 5-D TMA box
+// forward CTA (64 + 32*EW threads): warp 0 = TMA producer (one lane), warp 1 = TMEM alloc + tcgen05.mma issuer (one
+// lane), EW = 4 or 8 epilogue warps.  A tile = 128 output pixels x 64 channels, fetched per tap as ONE 5-D TMA box
 // (c, w, h, d, n) whose start coordinate carries the tap's shift; out-of-bounds = zero fill = the conv padding.
-// B tile = BN couts x 64 channels, a 2-D box of the prepared weights.  K-major, 128B-swizzled, 2-4 stage ring.
+// B tile = BN couts x 64 channels, a 2-D box of the prepared weights.  K-major, 128B-swizzled, 2-5 stage ring.
+// Variants (template parameters, chosen per shape in tma_fwd_launch_ex): CG = 2 CTA pairs (cta_group::2, 256-row tiles,
+// each CTA stages half of B), OCC = 2 co-resident CTAs for short reductions, PERSIST = strided tile walk per SM pair,
+// plain / ConvGRU epilogues; the measured bound that drives these choices is the ~64 B/clk an SM can ingest
+// (profiles/r1/README.md).
 //
 // wgrad CTA: D[ci][co] += sum_pixels X[pix + tap][ci] * dY[pix][co]: both operands are MN-major views of the same
-// channels-last planes (k = 64 consecutive pixels = one TMA box), one tap and one pixel range per CTA.
+// channels-last planes (k = 64 consecutive pixels = one TMA box), one tap and one pixel range per CTA (pair: 256 ci),
+// taps fastest in the grid so that a wave of CTAs re-uses one pixel range from L2.
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -1207,9 +1212,9 @@ static bool lo_fp16_enabled() {
 }
 constexpr int PROMOTE_MIN = 16;
 
-// Cluster shape (cm m-tiles x cn n-tiles) for operand multicast.  The main loop is bound by the L2 -> SM fabric
-// (64 KB of operand planes per 128x128x64 k-block at cm = cn = 1, see profiles/); a cm x cn cluster cuts the bytes
-// each CTA pulls from L2 to 32/cn + 32/cm KB.  env DVD_TC_CLUSTER="cm,cn" overrides (1,1 = off).
+// Cluster shape (cm m-tiles x cn n-tiles) for TMA operand multicast: a cm x cn cluster cuts the bytes each CTA pulls
+// from L2 to 32/cn + 32/cm KB per k-block.  Measured (profiles/r1/exp_multicast_clusters.txt): no gain, the bytes still
+// have to enter every SM, so it is OFF unless env DVD_TC_CLUSTER="cm,cn" asks for it; CTA pairs are the lever instead.
 static void cluster_override(int* cm, int* cn) {
   static int ocm = -1, ocn = -1;
   if (ocm < 0) {
