@@ -179,6 +179,11 @@ def run_b200(a):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # exactly ONE line on stdout: libraries (NCCL prints its version there) write to fd 1 too, so park the real stdout
+    # and point fd 1 at stderr until the JSON line is ready
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
     torch.cuda.set_device(local)
@@ -300,7 +305,8 @@ def run_b200(a):
         if world == 1 and not a.no_cpu_baseline:
             v, cores, sample, _ = cpu_step_time(a, 1, 0, a.cpu_frames)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 
