@@ -1,10 +1,13 @@
 #!/usr/bin/env python
 """Benchmark of the DVD-GAN G + Ds + Dt training step (BASELINE.json metric: clips/sec, 48f x 64x64).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config 2|3|4|5]
 
-One rank per GPU (torchrun sets RANK/LOCAL_RANK/WORLD_SIZE); each rank trains on its own shard of
-`--batch` clips (weak scaling), gradients are all-reduced over NCCL.  Rank 0 prints ONE JSON line.
+One rank per GPU (torchrun sets RANK/LOCAL_RANK/WORLD_SIZE; without it `--gpus N` > 1 re-launches itself under
+torchrun).  Weak scaling by default: every rank trains on `--batch` clips (global batch = batch x N); with
+`--global-batch G` the G clips are divided over the ranks (strong scaling, the reference's DataParallel split).
+Gradients are summed over NCCL.  Rank 0 prints ONE JSON line.  `--config` selects a BASELINE.json configuration
+(frame size / clip length / classes / per-GPU batch); the default is configs[1], the one the metric is quoted on.
 
   value     clips/s with the step's real clips already resident in HBM (device-timed, max over ranks)
   e2e       clips/s through Trainer.train_step with the clips in pinned HOST memory: H2D copy of the
@@ -28,16 +31,51 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-METRIC = "clips/sec (48f x 64x64) G+Ds+Dt step"
 UNIT = "clips/s"
-STEP_TFLOP_PER_CLIP = 8.187     # 3*G_fwd + 9*(Ds_fwd + Dt_fwd), 2*MAC
-STEP_HBM_GB_PER_CLIP = 4.42     # SURVEY.md 8(d), compulsory traffic under ideal fusion, fwd+bwd
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel from the committed `ncu --set full`
-# capture (profiles/): the per-timestep h-half update|reset GEMM of the 32x32 ConvGRU stage, B = 64
-NCU_TRAFFIC_BYTES = 173.7e6
-NCU_TRAFFIC_OF = ("conv_tma_fwd_kernel<256,0,2,1,8,1> (persistent CTA pairs), M=65536 Cin=256 Cout=512 5x5: dram 81.7 MB read + "
-                  "92.0 MB write per launch vs 214 MB algorithmic (67 MB operand planes, mostly still in L2 from the split "
-                  "kernel, + 13 MB weight planes + 134 MB fp32 output); profiles/r1/README.md")
+# algorithmic work (2*MAC; 3*G_fwd + 9*(Ds_fwd + Dt_fwd)) and compulsory HBM traffic under ideal
+# fusion, per clip and step, for the BASELINE.json configurations; other shapes report no step-level roofline.
+CONFIGS = {
+    # name: (frames, latent_dim, classes, batch per GPU, k, step TFLOP per clip, step HBM GB per clip, GPUs quoted)
+    2: dict(frames=48, latent_dim=4, classes=101, batch=64, k_sample=8, tflop=8.187, hbm_gb=4.42, gpus=1),
+    3: dict(frames=48, latent_dim=8, classes=101, batch=32, k_sample=8, tflop=32.76, hbm_gb=15.40, gpus=8),
+    4: dict(frames=12, latent_dim=16, classes=600, batch=8, k_sample=8, tflop=34.73, hbm_gb=16.5, gpus=1),
+    5: dict(frames=128, latent_dim=4, classes=101, batch=16, k_sample=8, tflop=21.60, hbm_gb=20.8, gpus=4),
+}
+NCU_TRAFFIC_FILE = os.path.join(ROOT, "profiles", "ncu_traffic.json")     # written by profiles/summarize_ncu.py
+
+
+def metric_name(a):
+    side = 16 * a.latent_dim
+    return f"clips/sec ({a.frames}f x {side}x{side}) G+Ds+Dt step"
+
+
+def workload_name(a, batch_per_gpu, world):
+    side = 16 * a.latent_dim
+    cfg = next((k for k, c in CONFIGS.items() if (c["frames"], c["latent_dim"], c["classes"]) ==
+                (a.frames, a.latent_dim, a.classes)), None)
+    tag = f"BASELINE.json configs[{cfg - 1}]" if cfg else "custom shape"
+    return (f"{tag}: {a.frames}f {side}x{side}, {a.classes} classes, batch={batch_per_gpu}/GPU x {world} GPU, ch={a.ch}, "
+            f"k={a.k_sample}, hinge, Adam(5e-5,(0,0.9)), full G+Ds+Dt step (3 optimizer steps"
+            + (", NCCL grad all-reduce)" if world > 1 else ")"))
+
+
+def step_work(a):
+    """(TFLOP, HBM GB) per clip and step from SURVEY 8(d), or (None, None) off the BASELINE shapes."""
+    for c in CONFIGS.values():
+        if (c["frames"], c["latent_dim"], c["classes"], c["k_sample"]) == (a.frames, a.latent_dim, a.classes, a.k_sample) \
+                and a.ch == 32:
+            return c["tflop"], c["hbm_gb"]
+    return None, None
+
+
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed `ncu --set
+    full` capture (profiles/summarize_ncu.py writes the file next to the CSV export it was read from)."""
+    try:
+        t = json.load(open(NCU_TRAFFIC_FILE))
+        return t["conv_tma_fwd"]["dram_bytes_per_launch"], t["conv_tma_fwd"]["source"]
+    except Exception:
+        return None, "no committed ncu capture found (profiles/ncu_traffic.json)"
 
 
 def parse():
@@ -46,18 +84,30 @@ def parse():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=64, help="clips per GPU (BASELINE.json configs[1]: 64)")
-    ap.add_argument("--frames", type=int, default=48)
-    ap.add_argument("--k-sample", type=int, default=8)
-    ap.add_argument("--classes", type=int, default=101)
+    ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS),
+                    help="BASELINE.json configuration (1-based): 2 = 48f 64x64 B=64 (default, the metric's), 3 = 48f "
+                         "128x128 B=32/GPU (quoted on 8 GPUs), 4 = 12f 256x256 600 classes, 5 = 128f 64x64 (4 GPUs)")
+    ap.add_argument("--batch", type=int, default=None, help="clips per GPU (default: the configuration's)")
+    ap.add_argument("--global-batch", type=int, default=None,
+                    help="strong scaling: this many clips in total, divided over the ranks")
+    ap.add_argument("--frames", type=int, default=None)
+    ap.add_argument("--k-sample", type=int, default=None)
+    ap.add_argument("--classes", type=int, default=None)
     ap.add_argument("--ch", type=int, default=32)
-    ap.add_argument("--latent-dim", type=int, default=4, help="frame side = 16 * latent_dim (4: 64x64; 8: configs[2]; "
-                                                             "16: configs[3])")
+    ap.add_argument("--latent-dim", type=int, default=None, help="frame side = 16 * latent_dim")
+    ap.add_argument("--gru-lean", default="auto", choices=["auto", "on", "off"],
+                    help="ConvGRU BPTT keeps h only and recomputes the gates (auto: when the full state would not fit)")
+    ap.add_argument("--shard-optimizer", action="store_true", help="reduce-scatter -> sharded Adam -> all-gather")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-frames", type=int, default=None, help="debug: shrink the CPU sample")
     ap.add_argument("--prof-dump", default=None, help="write the per-shape launch table of the timed steps here")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only (ncu launch list): skip the e2e leg")
-    return ap.parse_args()
+    a = ap.parse_args()
+    c = CONFIGS[a.config]
+    for k in ("frames", "latent_dim", "classes", "k_sample", "batch"):
+        if getattr(a, k) is None:
+            setattr(a, k, c[k])
+    return a
 
 
 def peaks():
@@ -73,7 +123,8 @@ def make_cfg(a, batch):
         adv_loss="hinge", z_dim=120, g_chn=a.ch, ds_chn=a.ch, dt_chn=a.ch, n_frames=a.frames,
         k_sample=a.k_sample, n_class=a.classes, batch_size=batch, d_iters=1, g_lr=5e-5, d_lr=5e-5, beta1=0.0,
         beta2=0.9, lr_schr="const", lr_decay=0.9999, total_epoch=1, log_epoch=10 ** 9, test_batch_size=1,
-        pretrained_model=None, version="bench", model_save_path="/tmp/dvd_bench", latent_dim=a.latent_dim)
+        pretrained_model=None, version="bench", model_save_path="/tmp/dvd_bench", latent_dim=a.latent_dim,
+        gru_lean={"auto": "auto", "on": True, "off": False}[a.gru_lean], shard_optimizer=a.shard_optimizer)
 
 
 # ----------------------------------------------------------------------------------------------- CPU arm
@@ -103,8 +154,8 @@ def cpu_step_time(a, steps, warmup, frames=None):
     for _ in range(steps):
         tr.step(clip, lab)
     dt = (time.perf_counter() - t0) / steps
-    sample = f"{steps} full G+Ds+Dt step(s) of {B} clip x {T}f x 64x64, k={min(a.k_sample, T)}, {a.classes} classes, " \
-             f"ch={a.ch}, fp32, {warmup} warm-up"
+    sample = f"{steps} full G+Ds+Dt step(s) of {B} clip x {T}f x {side}x{side}, k={min(a.k_sample, T)}, " \
+             f"{a.classes} classes, ch={a.ch}, fp32, {warmup} warm-up"
     return B / dt, cores, sample, dt
 
 
@@ -115,11 +166,11 @@ def run_reference(a):
     # warm-ups are full steps too (~10-25 s each on 8-16 cores); cap them so the run ends within minutes
     v, cores, sample, dt = cpu_step_time(a, a.steps, min(a.warmup, 1), a.cpu_frames)
     line = {
-        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+        "impl": "reference", "metric": metric_name(a), "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"config[1]: {a.frames}f 64x64, {a.classes} classes, ch={a.ch}, k={a.k_sample}; "
-                               "CPU sample = 1 clip per step", "timing": "host wall clock"},
+        "config": {"workload": workload_name(a, a.batch, max(a.gpus, 1)) + "; CPU sample = 1 clip per step",
+                   "timing": "host wall clock"},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -193,14 +244,21 @@ def run_b200(a):
         dist.init_process_group("nccl", device_id=dev)
     lib = _C.lib()
     pk, pk_kind = peaks()
-    B, T = a.batch, a.frames
-    torch.manual_seed(1234 + rank)
-    tr = Trainer(None, make_cfg(a, B))
+    T = a.frames
+    if a.global_batch:
+        if a.global_batch % world:
+            raise SystemExit(f"--global-batch {a.global_batch} is not divisible by {world} ranks")
+        B = a.global_batch // world
+    else:
+        B = a.batch
+    torch.manual_seed(1234)              # one CPU generator stream for every rank (Trainer broadcasts rank 0's anyway)
+    tr = Trainer(None, make_cfg(a, B * world))        # config.batch_size is the GLOBAL batch
     tr.G.train(); tr.D_s.train(); tr.D_t.train()
     n_host = 2
     side = 16 * a.latent_dim
-    host_clips = [(torch.rand(B, 3, T, side, side) * 2 - 1).pin_memory() for _ in range(n_host)]
-    host_labels = [torch.randint(0, a.classes, (B,)).pin_memory() for _ in range(n_host)]
+    gen = torch.Generator().manual_seed(4321 + rank)          # each rank's own shard of "real" clips
+    host_clips = [(torch.rand(B, 3, T, side, side, generator=gen) * 2 - 1).pin_memory() for _ in range(n_host)]
+    host_labels = [torch.randint(0, a.classes, (B,), generator=gen).pin_memory() for _ in range(n_host)]
     dev_clips = [c.to(dev) for c in host_clips]
     dev_labels = [l.to(dev) for l in host_labels]
 
@@ -256,6 +314,8 @@ def run_b200(a):
     clocks = sampler.summary(w0, w1) if sampler else None
     sec_e2e = float("nan") if a.no_e2e else timed(step_e2e, a.steps)[0]
     mem_gb = torch.cuda.max_memory_allocated() / 2 ** 30
+    scratch_hw, _ = _C.scratch_bytes()          # operand planes live in the cudaMallocAsync pool, outside torch's allocator
+    bad_ids = _C.index_errors()
 
     if rank == 0:
         clips = B * world * a.steps
@@ -266,25 +326,28 @@ def run_b200(a):
         peak = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
         fma_peak = 148 * 128 * 2 * (clocks["sm_mhz"] or pk.get("sm_max_mhz", 1965.0)) * 1e6 / 1e12 \
             if clocks else None
+        tflop_clip, hbm_clip = step_work(a)
+        traffic, traffic_of = ncu_traffic()
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-            "ms_per_step": sec / a.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "metric": metric_name(a), "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": sec / a.steps * 1e3, "higher_is_better": True,
+            "scaling": "strong" if a.global_batch else "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"config[1]: {T}f {side}x{side}, {a.classes} classes, batch={B}/GPU, ch={a.ch}, "
-                                   f"k={a.k_sample}, hinge, Adam(5e-5,(0,0.9)), full G+Ds+Dt step "
-                                   "(3 optimizer steps, NCCL grad all-reduce if N>1)",
+            "config": {"workload": workload_name(a, B, world),
                        "global_batch": B * world, "l2": "inputs and activations are GBs per step (>> 126 MB L2)",
-                       "parallelism": f"dp{world}"},
+                       "parallelism": f"dp{world}", "gru_bptt_state": "h only, gates recomputed" if tr.gru_lean
+                       else "h + gates + r*h kept", "optimizer": "sharded (RS/Adam/AG)" if a.shard_optimizer and world > 1
+                       else "replicated (all-reduce + full Adam)"},
             "e2e": {"value": clips / sec_e2e, "unit": UNIT,
                     "h2d_bytes_per_step": host_clips[0].numel() * 4 + host_labels[0].numel() * 8 + B * 120 * 4 + B * 8,
                     "d2h_bytes_per_step": 12},
             "gpu_launches": int(launches),
             "roofline": {
                 "kernel": "conv_tma_fwd_kernel (tcgen05 implicit-GEMM conv forward + dgrad; operands split into two "
-                          "16-bit planes, 3 MMAs per algorithmic MAC, fp32 TMEM accumulators)", "bound": "tensor",
+                          "bf16 planes, 3 MMAs per algorithmic MAC, fp32 TMEM accumulators)", "bound": "tensor",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
                 "mma_tflops": 3.0 * achieved, "mma_frac": 3.0 * achieved / peak if peak else None,
-                "traffic": NCU_TRAFFIC_BYTES, "traffic_of": NCU_TRAFFIC_OF,
+                "traffic": traffic, "traffic_of": traffic_of,
                 "peak_source": f"{pk_kind} bf16_tflops_sustained",
                 "launches_per_step": k_n / a.steps, "avg_launch_ms": k_ms / k_n if k_n else None,
                 "share_of_step": k_ms * 1e-3 / sec,
@@ -295,11 +358,13 @@ def run_b200(a):
                 "breakdown_ms_per_step": {k: v[0] / a.steps for k, v in prof.items() if v[2] > 0},
                 "operand_prep_gbs": prof["operand_prep"][1] / (prof["operand_prep"][0] * 1e-3) / 1e9
                 if prof["operand_prep"][0] > 0 else None,
-                "step": {"tflops": STEP_TFLOP_PER_CLIP * value / world, "hbm_gbs": STEP_HBM_GB_PER_CLIP * value / world,
-                         "hbm_frac": STEP_HBM_GB_PER_CLIP * value / world / pk["hbm_gbs"]},
+                "step": {"tflops": tflop_clip * value / world, "hbm_gbs": hbm_clip * value / world,
+                         "hbm_frac": hbm_clip * value / world / pk["hbm_gbs"]} if tflop_clip else None,
             },
             "clocks": clocks,
-            "peak_mem_gib": mem_gb,
+            "peak_mem_gib": mem_gb + scratch_hw / 2 ** 30,
+            "peak_mem_detail_gib": {"torch_allocator": mem_gb, "operand_plane_pool_high_water": scratch_hw / 2 ** 30},
+            "out_of_range_class_ids": bad_ids,
             "last_losses": losses[-1] if losses else None,
         }
         if world == 1 and not a.no_cpu_baseline:
@@ -311,9 +376,25 @@ def run_b200(a):
         dist.destroy_process_group()
 
 
+def relaunch_under_torchrun(a):
+    """`python bench.py --gpus N` without torchrun: start the N ranks ourselves (one node, 127.0.0.1 rendezvous)."""
+    import socket
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={a.gpus}",
+           "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.abspath(__file__)] + sys.argv[1:]
+    raise SystemExit(subprocess.call(cmd))
+
+
 if __name__ == "__main__":
     args = parse()
     if args.impl == "reference":
         run_reference(args)
     else:
+        world_env = int(os.environ.get("WORLD_SIZE", "1"))
+        if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
+            relaunch_under_torchrun(args)
+        if args.gpus != world_env:
+            raise SystemExit(f"bench.py: --gpus {args.gpus} but WORLD_SIZE={world_env}")
         run_b200(args)

@@ -32,6 +32,9 @@ _SIGS = {
     "dvd_prof_dump": (I, [ctypes.c_char_p]),
     "dvd_prof_read": (I, [I, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
                           ctypes.POINTER(ctypes.c_longlong)]),
+    "dvd_set_option": (I, [ctypes.c_char_p, I]),
+    "dvd_get_option": (I, [ctypes.c_char_p, ctypes.POINTER(c_int)]),
+    "dvd_scratch_bytes": (I, [ctypes.POINTER(ctypes.c_longlong), ctypes.POINTER(ctypes.c_longlong)]),
     "dvd_conv_fwd": (I, [ctypes.POINTER(ConvDesc), P, P, P, P, P, P]),
     "dvd_conv_wgrad": (I, [ctypes.POINTER(ConvDesc), P, P, P, P]),
     "dvd_weight_pack": (I, [P, I, I, I, I, I, I, P, I, P, I, I, I, I, P]),
@@ -64,9 +67,10 @@ _SIGS = {
     "dvd_channel_sum": (I, [P, I, I, L, L, I, P, P, P]),
     "dvd_axpby": (I, [P, F, F, L, P, P]),
     "dvd_gather_flat": (I, [ctypes.POINTER(c_void_p), ctypes.POINTER(c_int64), ctypes.POINTER(c_int64), I, P, P]),
-    "dvd_embedding_fwd": (I, [P, P, I, I, P, P]),
-    "dvd_embedding_bwd": (I, [P, P, I, I, P, P]),
-    "dvd_dhead_fwd": (I, [P, I, I, I, I, P, P, P, P, P, P, P, P, P]),
+    "dvd_embedding_fwd": (I, [P, P, I, I, I, P, P]),
+    "dvd_embedding_bwd": (I, [P, P, I, I, I, P, P]),
+    "dvd_index_errors": (I, [ctypes.POINTER(ctypes.c_uint), I, P]),
+    "dvd_dhead_fwd": (I, [P, I, I, I, I, I, P, P, P, P, P, P, P, P, P]),
     "dvd_dhead_bwd": (I, [P, P, P, I, I, I, I, I, P, P, P, P, P, P, P, P, P, P]),
     "dvd_gan_loss_fwd": (I, [P, I, F, I, I, P, P]),
     "dvd_gan_loss_bwd": (I, [P, P, I, F, I, P, P]),
@@ -91,7 +95,40 @@ def lib():
             fn.restype = res
             fn.argtypes = args
         _lib = l
+        # A/B switches for experiments: DVD_OPTIONS="oneacc=1,pair=0" (the library itself never reads the environment)
+        for kv in filter(None, os.environ.get("DVD_OPTIONS", "").split(",")):
+            k, _, v = kv.partition("=")
+            set_option(k.strip(), int(v))
     return _lib
+
+
+def set_option(name, value):
+    l = _lib if _lib is not None else lib()
+    if l.dvd_set_option(name.encode(), int(value)) != 0:
+        raise ValueError(l.dvd_last_error().decode())
+
+
+def get_option(name):
+    v = c_int()
+    if lib().dvd_get_option(name.encode(), ctypes.byref(v)) != 0:
+        raise ValueError(lib().dvd_last_error().decode())
+    return v.value
+
+
+def index_errors(reset=True):
+    """Out-of-range class ids seen by the embedding / head kernels on the current device (synchronises)."""
+    n = ctypes.c_uint()
+    rc = lib().dvd_index_errors(ctypes.byref(n), int(reset), stream())
+    if rc != 0:
+        raise RuntimeError(lib().dvd_last_error().decode())
+    return n.value
+
+
+def scratch_bytes():
+    hw, res = ctypes.c_longlong(), ctypes.c_longlong()
+    if lib().dvd_scratch_bytes(ctypes.byref(hw), ctypes.byref(res)) != 0:
+        raise RuntimeError(lib().dvd_last_error().decode())
+    return hw.value, res.value
 
 
 def ptr(t):
@@ -114,8 +151,23 @@ def call(name, *args):
         raise RuntimeError(f"{name}: {l.dvd_last_error().decode()}")
 
 
-def require_cuda(*tensors):
+def _require(tensors, dtype, what):
     for t in tensors:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise RuntimeError("dvdgan_b200 ops run on a CUDA device only (there is no CPU fallback); "
                                "got a tensor on " + str(t.device))
+        if t.dtype is not dtype:
+            raise TypeError(f"dvdgan_b200 kernels read {what}; got {t.dtype} (cast it first)")
+
+
+def require_cuda(*tensors):
+    """Data tensors handed to the C ABI are raw ``const float*`` there: refuse host tensors (no CPU fallback) and any
+    dtype other than float32 instead of reinterpreting the bytes."""
+    _require(tensors, torch.float32, "float32 data")
+
+
+def require_index(*tensors):
+    """Index tensors (class ids, frame indices) are ``const int64_t*`` in the C ABI."""
+    _require(tensors, torch.int64, "int64 indices")

@@ -13,6 +13,24 @@ namespace dvd {
 extern thread_local char g_last_error[512];
 extern std::atomic<long long> g_launches;   // kernels launched by this library (bench.py reports it)
 
+// Process-wide tuning switches (dvd_set_option / dvd_get_option in the C ABI).  The defaults are the validated
+// configuration; the switches exist for A/B measurements and for the tests that cross-check one engine against another.
+enum Option {
+  OPT_SIMT_ONLY = 0,     // "simt_only":   fp32 FFMA conv engine for everything (default 0)
+  OPT_PAIR,              // "pair":        cta_group::2 CTA-pair tiles (1)
+  OPT_PERSIST,           // "persist":     persistent CTA pairs when there is more than one wave of tiles (1)
+  OPT_ONEACC,            // "oneacc":      persistent tiles accumulate all three MMA products into ONE fp32 TMEM
+                         //                accumulator and double-buffer it (epilogue hidden under the next tile)
+  OPT_OCC2,              // "occ2":        two CTAs per SM for short reductions on narrow tiles (1)
+  OPT_EPI_PREFETCH,      // "epi_prefetch": L2 prefetch of the epilogue operands late in the main loop (1)
+  OPT_GRU_FUSED,         // "gru_fused":   ConvGRU gate math in the h-half GEMM epilogues (1)
+  OPT_GRU_SHARE_PLANES,  // "gru_share_planes": BPTT gate-gradient planes shared by x-dgrad and the weight gradients (1)
+  OPT_GRU_BWD_PLANES,    // "gru_bwd_planes":  the BPTT elementwise kernels write those planes themselves (1)
+  OPT_FLASH_ATTN,        // "flash_attn":  tcgen05 attention that never materialises the N x N map (1)
+  OPT_COUNT
+};
+int get_option(int opt);
+
 // Optional CUDA-event profiling of the dense engines (category 0: conv fwd/dgrad, 1: wgrad).
 void prof_begin(int category, double flops, cudaStream_t st);
 void prof_end(int category, cudaStream_t st);
@@ -70,6 +88,15 @@ inline int num_sms() {
     cached_dev = dev;
   }
   return cached;
+}
+
+// One-time per-device setup (cudaFuncSetAttribute, mem-pool thresholds): returns whether the current device's bit was
+// already set, and sets it.  Devices >= 64 are configured on every call (harmless).
+inline bool device_bit_test_and_set(std::atomic<uint64_t>& bits) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return false;
+  const uint64_t bit = 1ull << dev;
+  return (bits.fetch_or(bit, std::memory_order_acq_rel) & bit) != 0;
 }
 
 template <typename T>

@@ -377,7 +377,6 @@ extern "C" int dvd_conv_fwd(const dvd_conv_desc* d, const float* x, const float*
   p.vecY = (p.DHW % 4 == 0) && ((reinterpret_cast<uintptr_t>(y) & 15) == 0) && (d->y_s1 % 4 == 0) &&
            (d->y_s2 % 4 == 0) && (d->y_cs % 4 == 0);
   if (tma_fwd_eligible(p)) return tma_fwd_launch(p, st);
-  if (tc_fwd_eligible(p)) return tc_fwd_launch(p, st);
   const int nsm = num_sms();
   // tile selection
   int tile;  // 0: 128x128  1: 128x64  2: 64x64  3: 256x16
@@ -558,7 +557,6 @@ extern "C" int dvd_conv_wgrad(const dvd_conv_desc* d, const float* x, const floa
   fill_common(p, d);
   p.x = x; p.y = const_cast<float*>(dy); p.w = nullptr; p.bias = nullptr; p.res = nullptr;
   if (tma_wgrad_eligible(p)) return tma_wgrad_launch(p, dwp, st);
-  if (tc_wgrad_eligible(p)) return tc_wgrad_launch(p, dwp, st);
   const int nsm = num_sms();
   const bool small = (d->Cin <= 64 && d->Cout <= 64);
   const int bc = small ? 64 : 128, bo = small ? 64 : 128;
@@ -859,4 +857,69 @@ extern "C" int dvd_prof_dump(const char* path) {
 }
 
 extern "C" const char* dvd_last_error(void) { return dvd::g_last_error; }
-extern "C" int dvd_abi_version(void) { return 1; }
+extern "C" int dvd_abi_version(void) { return 2; }
+
+// ---------------------------------------------------------------------------------------------
+// process-wide options
+// ---------------------------------------------------------------------------------------------
+namespace dvd {
+namespace {
+struct OptDef { const char* name; int def; };
+const OptDef kOptDefs[OPT_COUNT] = {
+    {"simt_only", 0}, {"pair", 1}, {"persist", 1}, {"oneacc", 0}, {"occ2", 1}, {"epi_prefetch", 1},
+    {"gru_fused", 1}, {"gru_share_planes", 1}, {"gru_bwd_planes", 1}, {"flash_attn", 1},
+};
+std::atomic<int> g_opts[OPT_COUNT];
+std::atomic<bool> g_opts_init{false};
+void opts_init() {
+  if (g_opts_init.load(std::memory_order_acquire)) return;
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lk(mu);
+  if (g_opts_init.load(std::memory_order_relaxed)) return;
+  for (int i = 0; i < OPT_COUNT; ++i) g_opts[i].store(kOptDefs[i].def, std::memory_order_relaxed);
+  g_opts_init.store(true, std::memory_order_release);
+}
+int opt_index(const char* name) {
+  for (int i = 0; i < OPT_COUNT; ++i)
+    if (strcmp(kOptDefs[i].name, name) == 0) return i;
+  return -1;
+}
+}  // namespace
+int get_option(int opt) {
+  opts_init();
+  return g_opts[opt].load(std::memory_order_relaxed);
+}
+}  // namespace dvd
+
+extern "C" int dvd_set_option(const char* name, int value) {
+  DVD_CHECK_ARG(name != nullptr);
+  dvd::opts_init();
+  const int i = dvd::opt_index(name);
+  if (i < 0) return dvd::fail("unknown option '%s' (%s:%d)", name, __FILE__, __LINE__);
+  dvd::g_opts[i].store(value, std::memory_order_relaxed);
+  return 0;
+}
+extern "C" int dvd_get_option(const char* name, int* value) {
+  DVD_CHECK_ARG(name != nullptr && value != nullptr);
+  dvd::opts_init();
+  const int i = dvd::opt_index(name);
+  if (i < 0) return dvd::fail("unknown option '%s' (%s:%d)", name, __FILE__, __LINE__);
+  *value = dvd::g_opts[i].load(std::memory_order_relaxed);
+  return 0;
+}
+
+// High-water mark (bytes) of the current device's default stream-ordered memory pool: the operand planes of the
+// tensor-core engine live there (cudaMallocAsync), next to whatever allocator the caller uses for its tensors.
+extern "C" int dvd_scratch_bytes(long long* high_water, long long* reserved) {
+  DVD_CHECK_ARG(high_water != nullptr && reserved != nullptr);
+  int dev = 0;
+  DVD_CUDA(cudaGetDevice(&dev));
+  cudaMemPool_t pool;
+  DVD_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+  uint64_t hw = 0, res = 0;
+  DVD_CUDA(cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemHigh, &hw));
+  DVD_CUDA(cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &res));
+  *high_water = (long long)hw;
+  *reserved = (long long)res;
+  return 0;
+}

@@ -1,17 +1,16 @@
 // TMA + tcgen05 implicit-GEMM convolution (forward / dgrad and weight gradient) for sm_100a.
 //
-// Operand preparation (HBM-bound, once per conv call): the fp32 NC(D)HW activation (or dY) is split into
-// bf16 hi/lo planes in channels-last layout [N][D][H][W][Cp] (ReLU / nearest-x2 upsample of the reference's
-// F.relu / F.interpolate fused in); the fp32 packed weights [tap][Cin][Cout] become [tap][CoutP][CinP] planes.
-// x = hi + lo/s.  Forward convolutions (activations x weights, bounded magnitudes) use fp16 planes: hi = fp16(x),
-// lo = fp16((x - hi) * 2^11), so hi + lo/2^11 = x to 2^-24.  Anything that touches gradients (dgrad, wgrad) needs
-// bf16's exponent range: hi = bf16(x), lo = bf16((x - hi) * 2^8), x to 2^-17.  (A and B of one tcgen05.mma must
-// share a format: mixed fp16/bf16 descriptors raise an illegal-instruction fault.)  The GEMM issues
-//   D_main += A_hi*B_hi ,   D_lo += A_lo*B_hi + A_hi*B_lo          (result = D_main + D_lo / s)
-// into separate fp32 TMEM accumulators (the many small cross terms stay out of the large accumulator).  The tensor core
-// truncates its accumulator on every add (measured: a bias of ~K/16 * 2^-25 relative, 1.4e-5 at K = 12800); the optional
-// PROMOTE mode (env DVD_TC_PROMOTE, off by default, <= 128-column tiles only) ping-pongs the main accumulator between two
-// TMEM regions in chunks of 8 k-blocks and drains each finished chunk into fp32 registers.
+// Operand preparation (HBM-bound, once per conv call): the fp32 NC(D)HW activation (or dY) is split into two bf16
+// planes in channels-last layout [N][D][H][W][Cp] (ReLU / nearest-x2 upsample of the reference's F.relu /
+// F.interpolate fused in); the fp32 packed weights [tap][Cin][Cout] become [tap][CoutP][CinP] planes.
+//   x = hi + lo,  hi = bf16(x),  lo = bf16(x - hi)          (16-17 significant bits, fp32's exponent range: no
+//                                                             saturation or underflow for any finite fp32 input)
+// The GEMM issues three bf16 MMAs per algorithmic MAC,  A_hi*B_hi,  A_lo*B_hi,  A_hi*B_lo,  into fp32 TMEM accumulators:
+//   two-accumulator kernels:   D_main += A_hi*B_hi ;  D_lo += A_lo*B_hi + A_hi*B_lo ;  result = D_main + D_lo
+//                              (the many small cross terms stay out of the large accumulator, whose adds truncate)
+//   ONEACC kernels:            D += all three.  Halves the TMEM footprint, which lets the persistent 256-wide CTA-pair
+//                              kernel keep TWO accumulator sets: the epilogue of tile i drains set i&1 while the MMAs of
+//                              tile i+1 fill the other one.
 //
 // forward CTA (64 + 32*EW threads): warp 0 = TMA producer (one lane), warp 1 = TMEM alloc + tcgen05.mma issuer (one
 // lane), EW = 4 or 8 epilogue warps.  A tile = 128 output pixels x 64 channels, fetched per tap as ONE 5-D TMA box
@@ -27,7 +26,6 @@
 // taps fastest in the grid so that a wave of CTAs re-uses one pixel range from L2.
 #include <cuda.h>
 #include <cuda_bf16.h>
-#include <cuda_fp16.h>
 
 #include <algorithm>
 #include <mutex>
@@ -62,6 +60,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "memory");
   } while (!done);
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -79,36 +80,12 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm,
       ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
-
-// multicast variants: the box lands at the same CTA-relative offset of every CTA in `mask`, and each of those
-// CTAs' mbarrier (same offset) receives the complete_tx
-__device__ __forceinline__ void tma_load_5d_mc(uint32_t dst, const CUtensorMap* tm, uint32_t bar, uint16_t mask, int c0,
-                                               int c1, int c2, int c3, int c4) {
-  asm volatile(
-      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster"
-      " [%0], [%1, {%4, %5, %6, %7, %8}], [%2], %3;"
-      ::"r"(dst), "l"(tm), "r"(bar), "h"(mask), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* tm, uint32_t bar, uint16_t mask, int c0,
-                                               int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster"
-      " [%0], [%1, {%4, %5}], [%2], %3;"
-      ::"r"(dst), "l"(tm), "r"(bar), "h"(mask), "r"(c0), "r"(c1)
-      : "memory");
-}
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ uint32_t cluster_ctaid_x() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctaid.x;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ uint32_t cluster_ctaid_y() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctaid.y;" : "=r"(r));
   return r;
 }
 
@@ -150,11 +127,9 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
   d |= (uint64_t)2 << 61;      // SWIZZLE_128B
   return d;
 }
-// kind::f16 instruction descriptor: D = f32, A/B = bf16 (fmt 1) or fp16 (fmt 0), M = 128, N = n;
-// mn_major: both operands MN-major
-__device__ __forceinline__ uint32_t make_idesc(int n, int mn_major, uint32_t a_fmt = 1, uint32_t b_fmt = 1,
-                                               int m = BM) {
-  uint32_t d = (1u << 4) | (a_fmt << 7) | (b_fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+// kind::f16 instruction descriptor: D = f32, A/B = bf16 (format 1), M = m, N = n; mn_major: both operands MN-major
+__device__ __forceinline__ uint32_t make_idesc(int n, int mn_major, int m) {
+  uint32_t d = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
   if (mn_major) d |= (1u << 15) | (1u << 16);
   return d;
 }
@@ -183,11 +158,6 @@ __device__ __forceinline__ void mma_commit_pair(uint32_t bar) {
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-// commit that arrives on the same barrier offset of every CTA in `mask` (operand stages shared through multicast)
-__device__ __forceinline__ void mma_commit_mc(uint32_t bar, uint16_t mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               ::"r"(bar), "h"(mask) : "memory");
-}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -200,6 +170,21 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
       : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// 8 consecutive fp32 -> 8 bf16 hi + 8 bf16 lo (x = hi + lo)
+__device__ __forceinline__ void bf16_split8(const float* v, uint4* hi, uint4* lo) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __nv_bfloat162 hp = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    const float2 hf = __bfloat1622float2(hp);
+    const __nv_bfloat162 lp = __floats2bfloat162_rn(v[2 * i] - hf.x, v[2 * i + 1] - hf.y);
+    h[i] = *reinterpret_cast<const uint32_t*>(&hp);
+    l[i] = *reinterpret_cast<const uint32_t*>(&lp);
+  }
+  *hi = make_uint4(h[0], h[1], h[2], h[3]);
+  *lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
 
 // ------------------------------------------------------------------------------------------------ operand prep
 // src: fp32, element (n, c, pix) at n1*s1 + n2*s2 + c*cs + srcpix(pix)   ->  dst planes [n][pix][Cp] bf16 hi / lo.
@@ -214,10 +199,7 @@ struct PrepP {
   int out_pix;       // rows per image in dst
   int W, HW, up;     // output W, H*W (for the upsample source map); up = 1: source is (H/2, W/2)
   int relu;
-  int fp16;          // 1: fp16 planes, lo = (x - hi) * 2^11 (forward operands); 0: bf16 planes, lo = (x - hi) * 2^8
 };
-
-constexpr float kLoScaleBf16 = 256.f, kLoScaleFp16 = 2048.f;
 
 __global__ void __launch_bounds__(256) prep_planes_kernel(const PrepP p) {
   __shared__ float tile[64][33];
@@ -257,168 +239,93 @@ __global__ void __launch_bounds__(256) prep_planes_kernel(const PrepP p) {
     const int px = tid >> 3, q = tid & 7;
     const int pix = pix0 + px;
     if (pix < p.out_pix) {
-      uint32_t h[4], l[4];
+      float v[8];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float a = tile[q * 8 + 2 * i][px], b = tile[q * 8 + 2 * i + 1][px];
-        if (p.fp16) {
-          const float lim = 65504.f;
-          const __half2 hp = __floats2half2_rn(fminf(fmaxf(a, -lim), lim), fminf(fmaxf(b, -lim), lim));
-          const float2 hf = __half22float2(hp);
-          const float ra = (a - hf.x) * kLoScaleFp16, rb = (b - hf.y) * kLoScaleFp16;
-          const __half2 lp = __floats2half2_rn(fminf(fmaxf(ra, -lim), lim), fminf(fmaxf(rb, -lim), lim));
-          h[i] = *reinterpret_cast<const uint32_t*>(&hp);
-          l[i] = *reinterpret_cast<const uint32_t*>(&lp);
-        } else {
-          const __nv_bfloat162 hp = __floats2bfloat162_rn(a, b);
-          const float2 hf = __bfloat1622float2(hp);
-          const __nv_bfloat162 lp = __floats2bfloat162_rn((a - hf.x) * kLoScaleBf16, (b - hf.y) * kLoScaleBf16);
-          h[i] = *reinterpret_cast<const uint32_t*>(&hp);
-          l[i] = *reinterpret_cast<const uint32_t*>(&lp);
-        }
-      }
+      for (int i = 0; i < 8; ++i) v[i] = tile[q * 8 + i][px];
+      uint4 h, l;
+      bf16_split8(v, &h, &l);
       const int64_t o = ((int64_t)n * p.out_pix + pix) * p.Cp + c0 + q * 8;
-      *reinterpret_cast<uint4*>(p.hi + o) = make_uint4(h[0], h[1], h[2], h[3]);
-      *reinterpret_cast<uint4*>(p.lo + o) = make_uint4(l[0], l[1], l[2], l[3]);
+      *reinterpret_cast<uint4*>(p.hi + o) = h;
+      *reinterpret_cast<uint4*>(p.lo + o) = l;
     }
   }
 }
 
-// ------------------------------------------------------------------------------------------------ forward kernel
+// ------------------------------------------------------------------------------------------------ shared pieces
 struct TileGeom {
   int bw, bh, bd, bn;      // box extents (w, h, d, images); bw*bh*bd*bn = rows per box
 };
 
-// ------------------------------------------------------------------------------------------------ shared pieces
-constexpr int CHUNK = 8;       // k-blocks per promoted chunk (8 * 64 / 16 = 32 accumulator adds)
 constexpr int LATE_ITERS = 24; // the epilogue's L2 prefetch starts this many k-blocks before the end of the main loop
                                // (earlier, the lines are evicted again by the operand stream of a long main loop)
 
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-
 constexpr int tmem_cols_for(int need) { return need <= 32 ? 32 : need <= 64 ? 64 : need <= 128 ? 128 : need <= 256 ? 256 : 512; }
 
-// barrier block: full[S] | empty[S] | accum | cfull[2] | cdrain[2] | tmem slot
+// barrier block: full[S] | empty[S] | accum[2] | late[2] | tfree[2] | tmem slot      (index 1 of the pairs is used by
+// the double-buffered persistent kernel only)
 template <int STAGES>
 struct Bars {
   uint64_t* base;
   __device__ uint64_t* full(int s) const { return base + s; }
   __device__ uint64_t* empty(int s) const { return base + STAGES + s; }
-  __device__ uint64_t* accum() const { return base + 2 * STAGES; }
-  __device__ uint64_t* cfull(int b) const { return base + 2 * STAGES + 1 + b; }
-  __device__ uint64_t* cdrain(int b) const { return base + 2 * STAGES + 3 + b; }
-  __device__ uint32_t* slot() const { return reinterpret_cast<uint32_t*>(base + 2 * STAGES + 5); }
-  __device__ uint64_t* late() const { return base + 2 * STAGES + 6; }     // "the main loop is about to finish"
-  __device__ uint64_t* tfree() const { return base + 2 * STAGES + 7; }    // persistent CTAs: accumulators read out
-  __device__ void init(uint32_t empty_count = 1, uint32_t drain_count = 128, uint32_t tfree_count = 128) const {
+  __device__ uint64_t* accum(int b) const { return base + 2 * STAGES + b; }           // "accumulator set b is complete"
+  __device__ uint64_t* late(int b) const { return base + 2 * STAGES + 2 + b; }        // "the main loop is about to finish"
+  __device__ uint64_t* tfree(int b) const { return base + 2 * STAGES + 4 + b; }       // "set b has been read out"
+  __device__ uint32_t* slot() const { return reinterpret_cast<uint32_t*>(base + 2 * STAGES + 6); }
+  __device__ void init(uint32_t tfree_count) const {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(smem_u32(full(s)), 1);
-      mbar_init(smem_u32(empty(s)), empty_count);      // one commit per CTA of the cluster that shares the stage
+      mbar_init(smem_u32(empty(s)), 1);
     }
-    mbar_init(smem_u32(accum()), 1);
-    mbar_init(smem_u32(late()), 1);
-    mbar_init(smem_u32(tfree()), tfree_count);
     for (int b = 0; b < 2; ++b) {
-      mbar_init(smem_u32(cfull(b)), 1);
-      mbar_init(smem_u32(cdrain(b)), drain_count);
+      mbar_init(smem_u32(accum(b)), 1);
+      mbar_init(smem_u32(late(b)), 1);
+      mbar_init(smem_u32(tfree(b)), tfree_count);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
 };
 
-// The single-thread MMA issue loop shared by the forward and wgrad kernels.
-//   TMEM columns: !PROMOTE: main [0,BN) lo [BN,2BN);  PROMOTE: main0 [0,BN) main1 [BN,2BN) lo [2BN,3BN)
-//   lbo/sbo: descriptor strides; kadv: start-address advance (16-byte units) per UMMA_K = 16 step
-template <int BN, bool PROMOTE, int STAGES, int STAGE_BYTES, int A_BYTES, int B_BYTES, int CG = 1>
-__device__ __forceinline__ void mma_issue_loop(uint8_t* smem, const Bars<STAGES>& bars, uint32_t tmem_base, int n_iters,
-                                               int mn_major, uint32_t lbo, uint32_t sbo, uint32_t kadv,
-                                               uint32_t fmt /* 0 = fp16 planes, 1 = bf16 planes */,
-                                               uint16_t commit_mask /* 0: this CTA only */, int& stage,
+// The single-thread MMA issue loop shared by the forward and wgrad kernels: n_iters k-blocks into the accumulator(s)
+// at TMEM columns main_col / lo_col (ONEACC: lo_col == main_col).  lbo/sbo: descriptor strides; kadv: start-address
+// advance (16-byte units) per UMMA_K = 16 step.  `buf` selects the accum / late barriers that are signalled.
+template <int BN, bool ONEACC, int STAGES, int STAGE_BYTES, int A_BYTES, int B_BYTES, int CG>
+__device__ __forceinline__ void mma_issue_loop(uint8_t* smem, const Bars<STAGES>& bars, uint32_t main_col,
+                                               uint32_t lo_col, int buf, int n_iters, int mn_major, uint32_t lbo,
+                                               uint32_t sbo, uint32_t kadv, int& stage,
                                                uint32_t& phase /* ring position, carried across tiles */) {
-  const uint32_t id_main = make_idesc(BN, mn_major, fmt, fmt, BM * CG);
-  const uint32_t id_lo1 = id_main, id_lo2 = id_main;
-  const uint32_t lo_col = tmem_base + (PROMOTE ? 2 * BN : BN);
+  const uint32_t idesc = make_idesc(BN, mn_major, BM * CG);
   const int late_it = n_iters > LATE_ITERS ? n_iters - LATE_ITERS : 0;
   for (int it = 0; it < n_iters; ++it) {
-    const int chunk = PROMOTE ? it / CHUNK : 0;
-    const bool first = PROMOTE ? (it % CHUNK == 0) : (it == 0);
-    if (PROMOTE && first && chunk >= 2) {        // the epilogue must have drained this region (chunk - 2)
-      mbar_wait(smem_u32(bars.cdrain(chunk & 1)), (uint32_t)(((chunk >> 1) - 1) & 1));
-      tc_fence_after();
-    }
     if (it == late_it) {          // tell the epilogue warps (of both CTAs of a pair) to start prefetching their operands
-      mbar_arrive(smem_u32(bars.late()));
-      if constexpr (CG == 2) mbar_arrive_cluster(mapa_rank(smem_u32(bars.late()), 1));
+      mbar_arrive(smem_u32(bars.late(buf)));
+      if constexpr (CG == 2) mbar_arrive_cluster(mapa_rank(smem_u32(bars.late(buf)), 1));
     }
     mbar_wait(smem_u32(bars.full(stage)), phase);
     tc_fence_after();
     const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
     const uint64_t a_hi = make_desc(sa, lbo, sbo), a_lo = make_desc(sa + A_BYTES, lbo, sbo);
     const uint64_t b_hi = make_desc(sa + 2 * A_BYTES, lbo, sbo), b_lo = make_desc(sa + 2 * A_BYTES + B_BYTES, lbo, sbo);
-    const uint32_t main_col = tmem_base + (PROMOTE ? (uint32_t)(chunk & 1) * BN : 0u);
 #pragma unroll
     for (int kk = 0; kk < BKC / 16; ++kk) {
       const uint64_t adv = (uint64_t)(kk * kadv);
+      const uint32_t not_first = (it | kk) != 0;
       if constexpr (CG == 2) {
-        mma_f16_pair(main_col, a_hi + adv, b_hi + adv, id_main, !(first && kk == 0));
-        mma_f16_pair(lo_col, a_lo + adv, b_hi + adv, id_lo1, (it | kk) != 0);
-        mma_f16_pair(lo_col, a_hi + adv, b_lo + adv, id_lo2, 1);
+        mma_f16_pair(main_col, a_hi + adv, b_hi + adv, idesc, not_first);
+        mma_f16_pair(lo_col, a_lo + adv, b_hi + adv, idesc, ONEACC ? 1u : not_first);
+        mma_f16_pair(lo_col, a_hi + adv, b_lo + adv, idesc, 1);
       } else {
-        mma_f16(main_col, a_hi + adv, b_hi + adv, id_main, !(first && kk == 0));
-        mma_f16(lo_col, a_lo + adv, b_hi + adv, id_lo1, (it | kk) != 0);
-        mma_f16(lo_col, a_hi + adv, b_lo + adv, id_lo2, 1);
+        mma_f16(main_col, a_hi + adv, b_hi + adv, idesc, not_first);
+        mma_f16(lo_col, a_lo + adv, b_hi + adv, idesc, ONEACC ? 1u : not_first);
+        mma_f16(lo_col, a_hi + adv, b_lo + adv, idesc, 1);
       }
     }
-    if constexpr (CG == 2) {
-      mma_commit_pair(smem_u32(bars.empty(stage)));
-      if (PROMOTE && ((it % CHUNK) == CHUNK - 1 || it == n_iters - 1)) mma_commit_pair(smem_u32(bars.cfull(chunk & 1)));
-    } else {
-      if (commit_mask) mma_commit_mc(smem_u32(bars.empty(stage)), commit_mask);
-      else mma_commit(smem_u32(bars.empty(stage)));
-      if (PROMOTE && ((it % CHUNK) == CHUNK - 1 || it == n_iters - 1)) mma_commit(smem_u32(bars.cfull(chunk & 1)));
-    }
+    if constexpr (CG == 2) mma_commit_pair(smem_u32(bars.empty(stage)));
+    else mma_commit(smem_u32(bars.empty(stage)));
     if (++stage == STAGES) { stage = 0; phase ^= 1; }
   }
-  if (!PROMOTE) {
-    if constexpr (CG == 2) mma_commit_pair(smem_u32(bars.accum()));
-    else mma_commit(smem_u32(bars.accum()));
-  }
-}
-
-// PROMOTE epilogue: drain every finished chunk of the main accumulator into fp32 registers, then add lo / 256.
-// taddr = tmem_base + (lane quarter << 16).  All 128 epilogue threads call this.
-template <int BN, int STAGES, int CG = 1>
-__device__ __forceinline__ void collect_promoted(const Bars<STAGES>& bars, uint32_t taddr, int n_iters, float lo_inv,
-                                                 float* acc) {
-#pragma unroll
-  for (int j = 0; j < BN; ++j) acc[j] = 0.f;
-  const int n_chunks = (n_iters + CHUNK - 1) / CHUNK;
-  for (int c = 0; c < n_chunks; ++c) {
-    mbar_wait(smem_u32(bars.cfull(c & 1)), (uint32_t)((c >> 1) & 1));
-    tc_fence_after();
-#pragma unroll
-    for (int cb = 0; cb < BN; cb += 32) {
-      uint32_t r[32];
-      tmem_ld32(taddr + (uint32_t)(c & 1) * BN + cb, r);
-      tmem_ld_wait();
-#pragma unroll
-      for (int j = 0; j < 32; ++j) acc[cb + j] += __uint_as_float(r[j]);
-    }
-    tc_fence_before();
-    if constexpr (CG == 2) mbar_arrive_cluster(mapa_rank(smem_u32(bars.cdrain(c & 1)), 0));   // the issuer is in rank 0
-    else mbar_arrive(smem_u32(bars.cdrain(c & 1)));
-  }
-  // every MMA (including the cross terms) has completed once the last chunk's commit has fired
-#pragma unroll
-  for (int cb = 0; cb < BN; cb += 32) {
-    uint32_t r[32];
-    tmem_ld32(taddr + 2 * BN + cb, r);
-    tmem_ld_wait();
-#pragma unroll
-    for (int j = 0; j < 32; ++j) acc[cb + j] = fmaf(__uint_as_float(r[j]), lo_inv, acc[cb + j]);
-  }
+  if constexpr (CG == 2) mma_commit_pair(smem_u32(bars.accum(buf)));
+  else mma_commit(smem_u32(bars.accum(buf)));
 }
 
 // CG = 1: one CTA per 128 x BN tile.  CG = 2: a CTA pair (cluster (2,1,1)) per 256 x BN tile: each CTA stages its own
@@ -428,17 +335,19 @@ __device__ __forceinline__ void collect_promoted(const Bars<STAGES>& bars, uint3
 // OCC = 2: two CTAs per SM (two-stage rings, <= 168 registers, 2 * BN <= 256 TMEM columns each) for short-K
 // convolutions, where one CTA's prologue / epilogue would otherwise leave the tensor pipe idle: the co-resident CTA's
 // main loop runs underneath it.
-template <int BN, bool PROMOTE, int CG = 1, int OCC = 1>
+template <int BN, int CG, int OCC, bool PERSIST, bool ONEACC>
 struct Cfg {
   static constexpr int A_BYTES = BM * 128;
   static constexpr int B_BYTES = (BN / CG) * 128;
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
   static constexpr int STAGES_FIT = (OCC == 2 ? 108 * 1024 : 200 * 1024) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_FIT > 5 ? 5 : STAGES_FIT;
-  static_assert(OCC == 1 || (!PROMOTE && BN <= 128), "two CTAs per SM share 512 TMEM columns");
   static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 256;
-  static constexpr int TMEM_COLS = tmem_cols_for(PROMOTE ? 3 * BN : 2 * BN);
-  static_assert(!PROMOTE || BN <= 128, "promotion needs three accumulator regions");
+  static constexpr int NBUF = (PERSIST && ONEACC) ? 2 : 1;          // accumulator sets
+  static constexpr int SET_COLS = ONEACC ? BN : 2 * BN;             // TMEM columns of one set
+  static constexpr int TMEM_COLS = tmem_cols_for(NBUF * SET_COLS);
+  static_assert(NBUF * SET_COLS <= 512, "TMEM has 512 columns");
+  static_assert(OCC == 1 || TMEM_COLS <= 256, "two CTAs per SM share 512 TMEM columns");
   static_assert(STAGES >= 2, "pipeline needs two stages");
 };
 
@@ -446,67 +355,49 @@ struct FwdP {
   ConvP c;
   TileGeom g;
   int CoutP;
-  int fp16;             // operand planes are fp16 (forward values) rather than bf16 (anything with gradients)
-  float lo_inv;         // 1 / scale of the low-order planes
-  int cm, cn;           // CG = 1 only: cluster = cm m-tiles x cn n-tiles, the A tile is multicast to the cn CTAs of an
-                        // m-tile (each loads 1/cn of its rows), the B tile to the cm CTAs of an n-tile
   GruEpi gru;           // ConvGRU gate / state epilogue (mode 0: plain conv epilogue)
-  int prefetch;         // epilogue operands are prefetched into L2 late in the main loop (env DVD_TC_EPI_PREFETCH=0: off)
+  int prefetch;         // epilogue operands are prefetched into L2 late in the main loop
   int nt, tiles;        // persistent kernels: n-tiles and total (m-unit, n-tile) tiles
   int a_c_off;          // first channel of the A operand inside (shared) planes
 };
 
-// 32 consecutive channels of one pixel -> fp16 hi / lo planes (same split as prep_planes_kernel, fp16 = 1)
-__device__ __forceinline__ void store_planes32(__half* hi, __half* lo, const float* v) {
-  const float lim = 65504.f;
+// 32 consecutive channels of one pixel -> bf16 hi / lo planes (same split as prep_planes_kernel)
+__device__ __forceinline__ void store_planes32(__nv_bfloat16* hi, __nv_bfloat16* lo, const float* v) {
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
-    uint32_t h[4], l[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float a = v[q * 8 + 2 * i], b = v[q * 8 + 2 * i + 1];
-      const __half2 hp = __floats2half2_rn(fminf(fmaxf(a, -lim), lim), fminf(fmaxf(b, -lim), lim));
-      const float2 hf = __half22float2(hp);
-      const float ra = (a - hf.x) * kLoScaleFp16, rb = (b - hf.y) * kLoScaleFp16;
-      const __half2 lp = __floats2half2_rn(fminf(fmaxf(ra, -lim), lim), fminf(fmaxf(rb, -lim), lim));
-      h[i] = *reinterpret_cast<const uint32_t*>(&hp);
-      l[i] = *reinterpret_cast<const uint32_t*>(&lp);
-    }
-    reinterpret_cast<uint4*>(hi)[q] = make_uint4(h[0], h[1], h[2], h[3]);
-    reinterpret_cast<uint4*>(lo)[q] = make_uint4(l[0], l[1], l[2], l[3]);
+    uint4 h, l;
+    bf16_split8(v + q * 8, &h, &l);
+    reinterpret_cast<uint4*>(hi)[q] = h;
+    reinterpret_cast<uint4*>(lo)[q] = l;
   }
 }
 
-// EW = epilogue warps: 4 (one per TMEM lane quarter) or 8 (two per quarter, alternating 32-column chunks) -- the
-// wide tiles hold the only accumulator set of the SM, so the tensor pipe idles until the epilogue is through.
+// EW = epilogue warps: 4 (one per TMEM lane quarter) or 8 (two per quarter, alternating 32-column chunks).
 // PERSIST: one CTA (pair) per SM (pair) walks tiles t = cluster, cluster + #clusters, ... ; the TMA ring keeps running
-// into the next tile while the epilogue drains the accumulators (single TMEM set: the MMAs of the next tile wait for
-// `tfree`), and barrier setup / TMEM allocation / tensor-map fetch are paid once per SM instead of once per tile.
-template <int BN, bool PROMOTE, int CG, int OCC, int EW, bool PERSIST>
+// into the next tile while the epilogue drains the accumulators, and barrier setup / TMEM allocation / tensor-map fetch
+// are paid once per SM instead of once per tile.  With two accumulator sets (ONEACC) the MMAs of tile i+1 start as soon
+// as the set of tile i-1 has been read out; with one set they wait for the epilogue of tile i.
+template <int BN, int CG, int OCC, int EW, bool PERSIST, bool ONEACC>
 __global__ void __launch_bounds__(64 + 32 * EW, OCC)
 conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                     const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                     const FwdP fp) {
-  using C = Cfg<BN, PROMOTE, CG, OCC>;
+  using C = Cfg<BN, CG, OCC, PERSIST, ONEACC>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const Bars<C::STAGES> bars{reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES)};
   uint64_t* full_bar = bars.full(0);
   uint64_t* empty_bar = bars.empty(0);
-  uint64_t* accum_bar = bars.accum();
   uint32_t* tmem_slot = bars.slot();
 
   const ConvP& p = fp.c;
   const dvd_conv_desc& d = p.d;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int cm = CG == 2 ? 1 : fp.cm, cn = CG == 2 ? 1 : fp.cn;
-  const bool clustered = CG == 2 || cm * cn > 1;
-  const uint32_t cx = clustered ? cluster_ctaid_x() : 0u, cy = (clustered && CG == 1) ? cluster_ctaid_y() : 0u;
+  const uint32_t cx = CG == 2 ? cluster_ctaid_x() : 0u;
   const bool leader = CG == 1 || cx == 0;       // pair: rank 0 owns the full barriers and issues the MMAs
 
-  static_assert(EW == 4 || (EW == 8 && !PROMOTE), "the promoted accumulator is drained by exactly four warps");
-  static_assert(!PERSIST || (!PROMOTE && OCC == 1), "persistent tiles use the plain accumulator pair");
-  if (tid == 0) bars.init(CG == 2 ? 1u : (uint32_t)(cm * cn), CG == 2 ? 256u : 128u, (uint32_t)(32 * EW * CG));
+  static_assert(EW == 4 || EW == 8, "one or two epilogue warps per TMEM lane quarter");
+  if (tid == 0) bars.init((uint32_t)(32 * EW * CG));
   if (warp == 1) {
     if constexpr (CG == 2) {
       asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
@@ -520,7 +411,7 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
   }
   tc_fence_before();
   __syncthreads();
-  if (clustered) cluster_sync_all();        // peers' barriers are initialised before anything is signalled to them
+  if (CG == 2) cluster_sync_all();        // the peer's barriers are initialised before anything is signalled to them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -535,7 +426,7 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
   auto tile_origin = [&](int tile, int* m0, int* n0) {
     if (PERSIST) {
       const int nt = tile % fp.nt, mu = tile / fp.nt;
-      *m0 = (mu * CG + (int)(CG == 2 ? cx : 0u)) * BM;
+      *m0 = (mu * CG + (int)cx) * BM;
       *n0 = nt * BN;
     } else {
       *m0 = blockIdx.x * BM;
@@ -550,20 +441,14 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
      for (int tile = tile_first; tile < tile_end; tile += tile_stride) {
       int m0, n0;
       tile_origin(tile, &m0, &n0);
-      // box origin of this CTA's slice of the A tile: rows [cy * BM/cn, +BM/cn) of the m-tile -> (image, z, y, x);
-      // the box covers (bn, bd, bh, bw) = BM/cn rows.  B slice: couts [cx * b_rows, +b_rows) of the n-tile.
-      const int a_rows = BM / cn, b_rows = CG == 2 ? BN / 2 : BN / cm;
-      const int ms = m0 + (int)cy * a_rows;
-      const int img = ms / p.DHW;
-      int rem = ms - img * p.DHW;
+      // box origin of this CTA's 128 rows of the A tile -> (image, z, y, x); B slice: this CTA's half of the n-tile
+      constexpr int b_rows = BN / CG;
+      const int img = m0 / p.DHW;
+      int rem = m0 - img * p.DHW;
       const int z0 = rem / p.HW;
       rem -= z0 * p.HW;
       const int y0 = rem / d.W;
       const int x0 = rem - y0 * d.W;
-      const uint32_t a_off = cy * (uint32_t)(a_rows * 128), b_off = CG == 2 ? 0u : cx * (uint32_t)(b_rows * 128);
-      uint16_t mask_a = 0;                                    // same m-tile (cluster x), every n-tile of the cluster
-      for (int y = 0; y < cn; ++y) mask_a |= (uint16_t)(1u << (cx + y * cm));
-      const uint16_t mask_b = (uint16_t)(((1u << cm) - 1u) << (cy * cm));     // same n-tile, every m-tile
       int tap = it_begin / p.ck;
       int cchunk = it_begin - tap * p.ck;
       for (int it = 0; it < n_iters; ++it) {
@@ -588,20 +473,10 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
           tma_load_2d_pair(sa + 2 * C::A_BYTES + C::B_BYTES, &tmB_lo, fbl, c0, brow);
         } else {
           mbar_expect_tx(fb, C::STAGE_BYTES);
-          if (cn > 1) {
-            tma_load_5d_mc(sa + a_off, &tmA_hi, fb, mask_a, ca, px, py, pz, img);
-            tma_load_5d_mc(sa + C::A_BYTES + a_off, &tmA_lo, fb, mask_a, ca, px, py, pz, img);
-          } else {
-            tma_load_5d(sa, &tmA_hi, fb, ca, px, py, pz, img);
-            tma_load_5d(sa + C::A_BYTES, &tmA_lo, fb, ca, px, py, pz, img);
-          }
-          if (cm > 1) {
-            tma_load_2d_mc(sa + 2 * C::A_BYTES + b_off, &tmB_hi, fb, mask_b, c0, brow);
-            tma_load_2d_mc(sa + 2 * C::A_BYTES + C::B_BYTES + b_off, &tmB_lo, fb, mask_b, c0, brow);
-          } else {
-            tma_load_2d(sa + 2 * C::A_BYTES, &tmB_hi, fb, c0, brow);
-            tma_load_2d(sa + 2 * C::A_BYTES + C::B_BYTES, &tmB_lo, fb, c0, brow);
-          }
+          tma_load_5d(sa, &tmA_hi, fb, ca, px, py, pz, img);
+          tma_load_5d(sa + C::A_BYTES, &tmA_lo, fb, ca, px, py, pz, img);
+          tma_load_2d(sa + 2 * C::A_BYTES, &tmB_hi, fb, c0, brow);
+          tma_load_2d(sa + 2 * C::A_BYTES + C::B_BYTES, &tmB_lo, fb, c0, brow);
         }
         if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         if (++cchunk == p.ck) { cchunk = 0; ++tap; }
@@ -614,14 +489,16 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
       int stage = 0, ti = 0;
       uint32_t phase = 0;
       for (int tile = tile_first; tile < tile_end; tile += tile_stride, ++ti) {
-        if (PERSIST && ti > 0) {        // the epilogue warps (of both CTAs of a pair) have read the previous tile out
-          mbar_wait(smem_u32(bars.tfree()), (uint32_t)((ti - 1) & 1));
+        const int buf = C::NBUF == 2 ? (ti & 1) : 0;
+        const int use = C::NBUF == 2 ? (ti >> 1) : ti;        // how many times this accumulator set has been filled
+        if (PERSIST && use > 0) {       // the epilogue warps (of both CTAs of a pair) have read the set's last tile out
+          mbar_wait(smem_u32(bars.tfree(buf)), (uint32_t)((use - 1) & 1));
           tc_fence_after();
         }
+        const uint32_t main_col = tmem_base + (uint32_t)(buf * C::SET_COLS);
         // K-major operands: LBO unused (16), SBO = 1024 (8 rows of 128 B), 32 bytes (2 units) per UMMA_K step
-        mma_issue_loop<BN, PROMOTE, C::STAGES, C::STAGE_BYTES, C::A_BYTES, C::B_BYTES, CG>(
-            smem, bars, tmem_base, n_iters, 0, 16, 1024, 2, fp.fp16 ? 0u : 1u,
-            (CG == 1 && clustered) ? (uint16_t)((1u << (cm * cn)) - 1u) : (uint16_t)0, stage, phase);
+        mma_issue_loop<BN, ONEACC, C::STAGES, C::STAGE_BYTES, C::A_BYTES, C::B_BYTES, CG>(
+            smem, bars, main_col, ONEACC ? main_col : main_col + BN, buf, n_iters, 0, 16, 1024, 2, stage, phase);
       }
     }
     __syncwarp();
@@ -634,7 +511,8 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
    for (int tile = tile_first; tile < tile_end; tile += tile_stride, ++ti) {
     int m0, n0;
     tile_origin(tile, &m0, &n0);
-    const uint32_t tpar = (uint32_t)(ti & 1);        // phase of the per-tile barriers (accum, late)
+    const int buf = C::NBUF == 2 ? (ti & 1) : 0;
+    const uint32_t tpar = (uint32_t)((C::NBUF == 2 ? (ti >> 1) : ti) & 1);     // phase of the set's barriers
     const int row = q * 32 + lane;
     const int m = m0 + row;
     const bool ok = m < p.M;
@@ -656,7 +534,7 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
       }
     }
     const bool lead = blockIdx.z == 0;
-    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * C::SET_COLS);
     // 32 output channels of this thread's pixel.  Everything that has to be READ (previous value for accumulate,
     // residual, bias) is fetched for all 32 channels before the first store: a load-add-store chain per channel
     // would serialise 256 DRAM round trips per tile (measured: +60 % on the per-timestep h-half GEMMs).
@@ -694,8 +572,8 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
 #pragma unroll
         for (int j = 0; j < 32; ++j) ge.out2[(int64_t)nb * ge.o2_s1 + (int64_t)(c0 + j) * p.DHW + pix] = o2[j];
         if (ge.pl_hi)
-          store_planes32(reinterpret_cast<__half*>(ge.pl_hi) + (int64_t)m * ge.pl_Cp + c0,
-                         reinterpret_cast<__half*>(ge.pl_lo) + (int64_t)m * ge.pl_Cp + c0, o2);
+          store_planes32(reinterpret_cast<__nv_bfloat16*>(ge.pl_hi) + (int64_t)m * ge.pl_Cp + c0,
+                         reinterpret_cast<__nv_bfloat16*>(ge.pl_lo) + (int64_t)m * ge.pl_Cp + c0, o2);
       }
     };
     auto emit32 = [&](int cb, const float* v) {
@@ -736,7 +614,7 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
     };
     // While the main loop runs these warps are idle: pull everything the epilogue will read into L2, so its loads pay
     // an L2 hit instead of a DRAM round trip per 32-channel chunk.
-    if (fp.prefetch && !p.atomic_out && (d.accumulate || ge.mode)) mbar_wait(smem_u32(bars.late()), tpar);
+    if (fp.prefetch && !p.atomic_out && (d.accumulate || ge.mode)) mbar_wait(smem_u32(bars.late(buf)), tpar);
     if (fp.prefetch && ok && !p.atomic_out && (d.accumulate || ge.mode)) {
       const int nb = m / p.DHW, pix = m - nb * p.DHW;
       const int cend = min(BN, d.Cout - n0);
@@ -755,40 +633,39 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
         }
       }
     }
-    if constexpr (PROMOTE) {
-      float acc[BN];
-      collect_promoted<BN, C::STAGES, CG>(bars, taddr, n_iters, fp.lo_inv, acc);
-      if (ok) {
+    mbar_wait(smem_u32(bars.accum(buf)), tpar);
+    tc_fence_after();
+    for (int cb = 0; cb < BN; cb += 32) {
+      if (n0 + cb >= d.Cout) break;
+      if (EW == 8 && ((cb >> 5) & 1) != half) continue;
+      float v[32];
+      if constexpr (ONEACC) {
+        uint32_t r0[32];
+        tmem_ld32(taddr + cb, r0);
+        tmem_ld_wait();
 #pragma unroll
-        for (int cb = 0; cb < BN; cb += 32) emit32(cb, acc + cb);
-      }
-    } else {
-      mbar_wait(smem_u32(accum_bar), tpar);
-      tc_fence_after();
-      for (int cb = 0; cb < BN; cb += 32) {
-        if (n0 + cb >= d.Cout) break;
-        if (EW == 8 && ((cb >> 5) & 1) != half) continue;
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r0[j]);
+      } else {
         uint32_t r0[32], r1[32];
         tmem_ld32(taddr + cb, r0);
         tmem_ld32(taddr + BN + cb, r1);
         tmem_ld_wait();
-        if (!ok) continue;
-        float v[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = fmaf(__uint_as_float(r1[j]), fp.lo_inv, __uint_as_float(r0[j]));
-        emit32(cb, v);
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r0[j]) + __uint_as_float(r1[j]);
       }
+      if (!ok) continue;
+      emit32(cb, v);
     }
     tc_fence_before();
-    if (PERSIST) {        // this thread's TMEM reads of the tile are complete: the next tile's MMAs may overwrite it
-      if constexpr (CG == 2) mbar_arrive_cluster(mapa_rank(smem_u32(bars.tfree()), 0));
-      else mbar_arrive(smem_u32(bars.tfree()));
+    if (PERSIST) {        // this thread's TMEM reads of the set are complete: a later tile's MMAs may overwrite it
+      if constexpr (CG == 2) mbar_arrive_cluster(mapa_rank(smem_u32(bars.tfree(buf)), 0));
+      else mbar_arrive(smem_u32(bars.tfree(buf)));
     }
    }
   }
 
   __syncthreads();
-  if (clustered) cluster_sync_all();        // no CTA leaves while a peer may still signal its barriers / read its smem
+  if (CG == 2) cluster_sync_all();        // no CTA leaves while the peer may still signal its barriers / read its smem
   if (warp == 1) {
     tc_fence_after();
     if constexpr (CG == 2)
@@ -804,12 +681,11 @@ struct WgP {
   ConvP c;
   TileGeom g;           // box of 64 pixels
   int nsplit, per_split;   // pixel range per CTA (multiple of 64)
-  int cm, cn;              // cluster = cm ci-blocks x cn co-blocks: the dY tile is multicast across cm, the X tile across cn
   int y_c_off;             // shared dY planes: channel offset, frames per clip in the planes, first frame, frames used
   int y_T, y_t_off, y_n2;  // (y_T = 0: the planes hold exactly this conv's images)
 };
 
-template <int BN, bool PROMOTE, int CG = 1>
+template <int BN, int CG>
 struct WCfg {
   static constexpr int A_BYTES = 2 * 64 * 128;           // 128 ci = two 64-wide MN blocks of [64 k][128 B]
   static constexpr int B_BLOCKS = BN / CG / 64;          // 64-wide co blocks staged by this CTA (pair: half of BN)
@@ -818,35 +694,31 @@ struct WCfg {
   static constexpr int STAGES_FIT = (200 * 1024) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_FIT > 5 ? 5 : STAGES_FIT;
   static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 256;
-  static constexpr int TMEM_COLS = tmem_cols_for(PROMOTE ? 3 * BN : 2 * BN);
-  static_assert(!PROMOTE || BN <= 128, "promotion needs three accumulator regions");
+  static constexpr int TMEM_COLS = tmem_cols_for(2 * BN);
   static_assert(BN % (64 * CG) == 0, "whole 64-wide co blocks per CTA");
 };
 
 // CG = 2: CTA pair = 256 ci x BN co; each CTA stages its own 128 ci of X and half of the dY blocks.
-template <int BN, bool PROMOTE, int CG>
+template <int BN, int CG>
 __global__ void __launch_bounds__(NT, 1)
 conv_tma_wgrad_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant__ CUtensorMap tmX_lo,
                       const __grid_constant__ CUtensorMap tmY_hi, const __grid_constant__ CUtensorMap tmY_lo,
                       const WgP wp, float* __restrict__ dwp) {
-  using C = WCfg<BN, PROMOTE, CG>;
+  using C = WCfg<BN, CG>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const Bars<C::STAGES> bars{reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES)};
   uint64_t* full_bar = bars.full(0);
   uint64_t* empty_bar = bars.empty(0);
-  uint64_t* accum_bar = bars.accum();
   uint32_t* tmem_slot = bars.slot();
 
   const ConvP& p = wp.c;
   const dvd_conv_desc& d = p.d;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int cm = CG == 2 ? 1 : wp.cm, cn = CG == 2 ? 1 : wp.cn;
-  const bool clustered = CG == 2 || cm * cn > 1;
-  const uint32_t cx = clustered ? cluster_ctaid_x() : 0u, cy = (clustered && CG == 1) ? cluster_ctaid_y() : 0u;
+  const uint32_t cx = CG == 2 ? cluster_ctaid_x() : 0u;
   const bool leader = CG == 1 || cx == 0;
 
-  if (tid == 0) bars.init(CG == 2 ? 1u : (uint32_t)(cm * cn), CG == 2 ? 256u : 128u);
+  if (tid == 0) bars.init(128u * CG);
   if (warp == 1) {
     if constexpr (CG == 2) {
       asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
@@ -860,7 +732,7 @@ conv_tma_wgrad_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_c
   }
   tc_fence_before();
   __syncthreads();
-  if (clustered) cluster_sync_all();
+  if (CG == 2) cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -882,9 +754,6 @@ conv_tma_wgrad_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_c
       const int kh = t2 % d.kH;
       const int kd = t2 / d.kH;
       const int ox = kw - d.kW / 2, oy = kh - d.kH / 2, oz = kd - d.kD / 2;
-      uint16_t mask_a = 0;                                    // same ci-block (cluster x), every co-block of the cluster
-      for (int y = 0; y < cn; ++y) mask_a |= (uint16_t)(1u << (cx + y * cm));
-      const uint16_t mask_b = (uint16_t)(((1u << cm) - 1u) << (cy * cm));     // same co-block, every ci-block
       int stage = 0;
       uint32_t phase = 0;
       for (int it = 0; it < n_iters; ++it) {
@@ -916,25 +785,16 @@ conv_tma_wgrad_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_c
           }
         } else {
           mbar_expect_tx(fb, C::STAGE_BYTES);
-          // each CTA loads 1/cn of the X blocks and 1/cm of the dY blocks and multicasts them to the CTAs sharing them
-          for (int b = (int)cy * (2 / cn); b < ((int)cy + 1) * (2 / cn); ++b) {
-            if (cn > 1) {
-              tma_load_5d_mc(sa + b * 8192, &tmX_hi, fb, mask_a, ci0 + b * 64, x0 + ox, y0 + oy, z0 + oz, img);
-              tma_load_5d_mc(sa + C::A_BYTES + b * 8192, &tmX_lo, fb, mask_a, ci0 + b * 64, x0 + ox, y0 + oy, z0 + oz, img);
-            } else {
-              tma_load_5d(sa + b * 8192, &tmX_hi, fb, ci0 + b * 64, x0 + ox, y0 + oy, z0 + oz, img);
-              tma_load_5d(sa + C::A_BYTES + b * 8192, &tmX_lo, fb, ci0 + b * 64, x0 + ox, y0 + oy, z0 + oz, img);
-            }
+#pragma unroll
+          for (int b = 0; b < 2; ++b) {
+            tma_load_5d(sa + b * 8192, &tmX_hi, fb, ci0 + b * 64, x0 + ox, y0 + oy, z0 + oz, img);
+            tma_load_5d(sa + C::A_BYTES + b * 8192, &tmX_lo, fb, ci0 + b * 64, x0 + ox, y0 + oy, z0 + oz, img);
           }
-          for (int b = (int)cx * (C::B_BLOCKS / cm); b < ((int)cx + 1) * (C::B_BLOCKS / cm); ++b) {
+#pragma unroll
+          for (int b = 0; b < C::B_BLOCKS; ++b) {
             const int yc = wp.y_c_off + co0 + b * 64;
-            if (cm > 1) {
-              tma_load_5d_mc(sa + 2 * C::A_BYTES + b * 8192, &tmY_hi, fb, mask_b, yc, x0, y0, z0, yimg);
-              tma_load_5d_mc(sa + 2 * C::A_BYTES + C::B_BYTES + b * 8192, &tmY_lo, fb, mask_b, yc, x0, y0, z0, yimg);
-            } else {
-              tma_load_5d(sa + 2 * C::A_BYTES + b * 8192, &tmY_hi, fb, yc, x0, y0, z0, yimg);
-              tma_load_5d(sa + 2 * C::A_BYTES + C::B_BYTES + b * 8192, &tmY_lo, fb, yc, x0, y0, z0, yimg);
-            }
+            tma_load_5d(sa + 2 * C::A_BYTES + b * 8192, &tmY_hi, fb, yc, x0, y0, z0, yimg);
+            tma_load_5d(sa + 2 * C::A_BYTES + C::B_BYTES + b * 8192, &tmY_lo, fb, yc, x0, y0, z0, yimg);
           }
         }
         if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
@@ -944,12 +804,11 @@ conv_tma_wgrad_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_c
   } else if (warp == 1) {
     if (lane == 0 && leader) {
       // MN-major operands: LBO = 8192 (next 64-wide MN block), SBO = 1024 (next 8 k-rows); one UMMA_K step =
-      // 16 k-rows of 128 B = 2048 B = 128 units.  dY is a gradient, so both operands use bf16 planes.
+      // 16 k-rows of 128 B = 2048 B = 128 units.
       int stage = 0;
       uint32_t phase = 0;
-      mma_issue_loop<BN, PROMOTE, C::STAGES, C::STAGE_BYTES, C::A_BYTES, C::B_BYTES, CG>(
-          smem, bars, tmem_base, n_iters, 1, 8192, 1024, 128, 1u,
-          (CG == 1 && clustered) ? (uint16_t)((1u << (cm * cn)) - 1u) : (uint16_t)0, stage, phase);
+      mma_issue_loop<BN, false, C::STAGES, C::STAGE_BYTES, C::A_BYTES, C::B_BYTES, CG>(
+          smem, bars, tmem_base, tmem_base + BN, 0, n_iters, 1, 8192, 1024, 128, stage, phase);
     }
     __syncwarp();
   } else {
@@ -958,42 +817,28 @@ conv_tma_wgrad_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_c
     const bool ok = ci < d.Cin;
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
     float* dst = dwp + ((int64_t)tap * d.Cin + ci) * d.Cout + co0;
-    if constexpr (PROMOTE) {
-      float acc[BN];
-      collect_promoted<BN, C::STAGES, CG>(bars, taddr, n_iters, 1.f / kLoScaleBf16, acc);
-      if (ok) {
+    mbar_wait(smem_u32(bars.accum(0)), 0);
+    tc_fence_after();
+    for (int cb = 0; cb < BN; cb += 32) {
+      if (co0 + cb >= d.Cout) break;
+      uint32_t r0[32], r1[32];
+      tmem_ld32(taddr + cb, r0);
+      tmem_ld32(taddr + BN + cb, r1);
+      tmem_ld_wait();
+      if (!ok) continue;
 #pragma unroll
-        for (int j = 0; j < BN; ++j) {
-          if (co0 + j < d.Cout) {
-            if (p.atomic_out) atomicAdd(dst + j, acc[j]);
-            else dst[j] = acc[j];
-          }
-        }
-      }
-    } else {
-      mbar_wait(smem_u32(accum_bar), 0);
-      tc_fence_after();
-      for (int cb = 0; cb < BN; cb += 32) {
-        if (co0 + cb >= d.Cout) break;
-        uint32_t r0[32], r1[32];
-        tmem_ld32(taddr + cb, r0);
-        tmem_ld32(taddr + BN + cb, r1);
-        tmem_ld_wait();
-        if (!ok) continue;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          if (co0 + cb + j >= d.Cout) break;
-          const float v = fmaf(__uint_as_float(r1[j]), 1.f / kLoScaleBf16, __uint_as_float(r0[j]));
-          if (p.atomic_out) atomicAdd(dst + cb + j, v);
-          else dst[cb + j] = v;
-        }
+      for (int j = 0; j < 32; ++j) {
+        if (co0 + cb + j >= d.Cout) break;
+        const float v = __uint_as_float(r0[j]) + __uint_as_float(r1[j]);
+        if (p.atomic_out) atomicAdd(dst + cb + j, v);
+        else dst[cb + j] = v;
       }
     }
     tc_fence_before();
   }
 
   __syncthreads();
-  if (clustered) cluster_sync_all();
+  if (CG == 2) cluster_sync_all();
   if (warp == 1) {
     tc_fence_after();
     if constexpr (CG == 2)
@@ -1011,7 +856,7 @@ typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void
 static EncodeFn get_encode() {
   static EncodeFn fn = nullptr;
   static std::once_flag once;
-  std::call_once(once, [] {
+  std::call_once(once, [] {          // a driver entry point: process-wide, not per device
     void* ptr = nullptr;
     cudaDriverEntryPointQueryResult q;
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
@@ -1080,13 +925,15 @@ static bool tile_geom(int rows, int N, int D, int H, int W, TileGeom* g) {
 
 static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 
+// Stream-ordered scratch for the operand planes of one call (cudaMallocAsync from the device's default pool; the pool
+// keeps freed blocks, dvd_scratch_bytes() reports its high-water mark so that callers can account for it).
 struct Scratch {
   void* ptr = nullptr;
   cudaStream_t st;
   int alloc(size_t bytes, cudaStream_t s) {
     st = s;
-    static std::once_flag once;
-    std::call_once(once, [] {
+    static std::atomic<uint64_t> pool_set{0};         // per device
+    if (!device_bit_test_and_set(pool_set)) {
       int dev = 0;
       cudaGetDevice(&dev);
       cudaMemPool_t pool;
@@ -1094,7 +941,7 @@ struct Scratch {
         uint64_t thr = UINT64_MAX;
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
       }
-    });
+    }
     DVD_CUDA(cudaMallocAsync(&ptr, bytes, s));
     return 0;
   }
@@ -1104,15 +951,13 @@ struct Scratch {
 };
 
 static int prep_planes(const float* src, int N1, int N2, int C, int Cp, int64_t s1, int64_t s2, int64_t cs, int in_pix,
-                       int out_pix, int W, int HW, int up, int relu, int fp16, __nv_bfloat16* hi, __nv_bfloat16* lo,
+                       int out_pix, int W, int HW, int up, int relu, __nv_bfloat16* hi, __nv_bfloat16* lo,
                        cudaStream_t st) {
   PrepP p;
   p.src = src; p.hi = hi; p.lo = lo; p.N2 = N2; p.C = C; p.Cp = Cp; p.s1 = s1; p.s2 = s2; p.cs = cs;
-  p.in_pix = in_pix; p.out_pix = out_pix; p.W = W; p.HW = HW; p.up = up; p.relu = relu; p.fp16 = fp16;
+  p.in_pix = in_pix; p.out_pix = out_pix; p.W = W; p.HW = HW; p.up = up; p.relu = relu;
   const int N = N1 * N2;
-  DVD_CHECK_ARG(N <= 65535 * 64);
-  // gridDim.z <= 65535: fold large image counts
-  DVD_CHECK_ARG(N <= 65535);
+  DVD_CHECK_ARG(N <= 65535);          // gridDim.z
   dim3 grid(ceil_div(out_pix, 32), Cp / 64, N);
   prof_tag("prep N%d pix%d C%d", N, out_pix, Cp);
   prof_begin(2, (double)N * out_pix * Cp * 8.0, st);          // "flops" = bytes moved (4 in + 4 out per element)
@@ -1122,143 +967,69 @@ static int prep_planes(const float* src, int N1, int N2, int C, int Cp, int64_t 
   return 0;
 }
 
-template <int BN, bool PROMOTE, int CG, int OCC = 1, int EW = 4, bool PERSIST = false>
+template <int BN, int CG, int OCC = 1, int EW = 4, bool PERSIST = false, bool ONEACC = false>
 static int launch_fwd(const CUtensorMap* m, const FwdP& fp, dim3 grid, cudaStream_t st) {
-  using C = Cfg<BN, PROMOTE, CG, OCC>;
+  using C = Cfg<BN, CG, OCC, PERSIST, ONEACC>;
   constexpr int NT = 64 + 32 * EW;
-  static bool configured = false;
-  if (!configured) {
-    DVD_CUDA(cudaFuncSetAttribute(conv_tma_fwd_kernel<BN, PROMOTE, CG, OCC, EW, PERSIST>,
+  static std::atomic<uint64_t> configured{0};         // one bit per device: the attribute is per (function, device)
+  if (!device_bit_test_and_set(configured))
+    DVD_CUDA(cudaFuncSetAttribute(conv_tma_fwd_kernel<BN, CG, OCC, EW, PERSIST, ONEACC>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
-    configured = true;
-  }
   if (PERSIST) {          // one CTA (pair) per SM (pair), or fewer when there are fewer tiles
     const int slots = num_sms() / CG;
     grid = dim3((unsigned)(CG * std::min(fp.tiles, slots)), 1, 1);
   }
-  const int cx = CG == 2 ? 2 : fp.cm, cy = CG == 2 ? 1 : fp.cn;
-  if (cx * cy > 1) {
+  if (CG == 2) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid; cfg.blockDim = dim3(NT); cfg.dynamicSmemBytes = C::SMEM; cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = cx; attr[0].val.clusterDim.y = cy; attr[0].val.clusterDim.z = 1;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    DVD_CUDA(cudaLaunchKernelEx(&cfg, conv_tma_fwd_kernel<BN, PROMOTE, CG, OCC, EW, PERSIST>, m[0], m[1], m[2], m[3], fp));
+    DVD_CUDA(cudaLaunchKernelEx(&cfg, conv_tma_fwd_kernel<BN, CG, OCC, EW, PERSIST, ONEACC>, m[0], m[1], m[2], m[3], fp));
   } else {
-    conv_tma_fwd_kernel<BN, PROMOTE, CG, OCC, EW, PERSIST><<<grid, NT, C::SMEM, st>>>(m[0], m[1], m[2], m[3], fp);
+    conv_tma_fwd_kernel<BN, CG, OCC, EW, PERSIST, ONEACC><<<grid, NT, C::SMEM, st>>>(m[0], m[1], m[2], m[3], fp);
   }
   return 0;
 }
-template <int BN, bool PROMOTE, int CG>
+template <int BN, int CG>
 static int launch_wgrad(const CUtensorMap* m, const WgP& wp, float* dwp, dim3 grid, cudaStream_t st) {
-  using C = WCfg<BN, PROMOTE, CG>;
-  static bool configured = false;
-  if (!configured) {
-    DVD_CUDA(cudaFuncSetAttribute(conv_tma_wgrad_kernel<BN, PROMOTE, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  C::SMEM));
-    configured = true;
-  }
-  const int cx = CG == 2 ? 2 : wp.cm, cy = CG == 2 ? 1 : wp.cn;
-  if (cx * cy > 1) {
+  using C = WCfg<BN, CG>;
+  static std::atomic<uint64_t> configured{0};
+  if (!device_bit_test_and_set(configured))
+    DVD_CUDA(cudaFuncSetAttribute(conv_tma_wgrad_kernel<BN, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+  if (CG == 2) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid; cfg.blockDim = dim3(NT); cfg.dynamicSmemBytes = C::SMEM; cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = cx; attr[0].val.clusterDim.y = cy; attr[0].val.clusterDim.z = 1;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    DVD_CUDA(cudaLaunchKernelEx(&cfg, conv_tma_wgrad_kernel<BN, PROMOTE, CG>, m[0], m[1], m[2], m[3], wp, dwp));
+    DVD_CUDA(cudaLaunchKernelEx(&cfg, conv_tma_wgrad_kernel<BN, CG>, m[0], m[1], m[2], m[3], wp, dwp));
   } else {
-    conv_tma_wgrad_kernel<BN, PROMOTE, CG><<<grid, NT, C::SMEM, st>>>(m[0], m[1], m[2], m[3], wp, dwp);
+    conv_tma_wgrad_kernel<BN, CG><<<grid, NT, C::SMEM, st>>>(m[0], m[1], m[2], m[3], wp, dwp);
   }
   return 0;
 }
 
-// accumulator policy.  The tensor core truncates its fp32 accumulator on every add (a bias of ~K/16 * 2^-25 relative:
-// 1.4e-5 at K = 12800, measured).  With PROMOTE (BN <= 128, three TMEM regions) the main accumulator is drained into
-// fp32 registers every 8 k-blocks; the 192/256-wide tiles that the SM-ingest roofline wants have no TMEM left for it.
-// env DVD_TC_PROMOTE: unset/"0" = never (default), "auto" = promote where the tile is <= 128 wide anyway, "1" = always
-// (caps tiles at 128 columns).  Measured at G's output (ch = 32, 48 frames): 1.3e-4 rel-L2 vs the fp32 reference with
-// promotion everywhere, 2.3e-4 without, the reference's own fp32-vs-fp64 error being 1.3e-4 (profiles/).
-static int promote_mode() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("DVD_TC_PROMOTE");
-    v = (!e || e[0] == '0') ? 0 : (e[0] == '1' ? 1 : 2);
-  }
-  return v;
-}
 // widest tile with the least padded columns (ties -> wider)
-static int pick_bn(int Cout, int max_bn, bool allow_192) {
+static int pick_bn(int Cout, bool allow_192) {
   if (Cout <= 64) return 64;
   const int cand[3] = {256, 192, 128};
   int best = 128, best_waste = 1 << 30;
   for (int i = 0; i < 3; ++i) {
     const int bn = cand[i];
-    if (bn > max_bn || (bn == 192 && !allow_192)) continue;
+    if (bn == 192 && !allow_192) continue;
     const int waste = (Cout + bn - 1) / bn * bn - Cout;
     if (waste < best_waste) { best = bn; best_waste = waste; }
   }
   return best;
 }
-// env DVD_TC_FMT=bf16 forces bf16 planes everywhere (default: fp16 planes for forward convolutions)
-static bool lo_fp16_enabled() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("DVD_TC_FMT");
-    v = (e && strcmp(e, "bf16") == 0) ? 0 : 1;
-  }
-  return v != 0;
-}
-constexpr int PROMOTE_MIN = 16;
-
-// Cluster shape (cm m-tiles x cn n-tiles) for TMA operand multicast: a cm x cn cluster cuts the bytes each CTA pulls
-// from L2 to 32/cn + 32/cm KB per k-block.  Measured (profiles/r1/exp_multicast_clusters.txt): no gain, the bytes still
-// have to enter every SM, so it is OFF unless env DVD_TC_CLUSTER="cm,cn" asks for it; CTA pairs are the lever instead.
-static void cluster_override(int* cm, int* cn) {
-  static int ocm = -1, ocn = -1;
-  if (ocm < 0) {
-    ocm = 0; ocn = 0;
-    const char* e = getenv("DVD_TC_CLUSTER");
-    if (e) sscanf(e, "%d,%d", &ocm, &ocn);
-  }
-  if (ocm > 0 && ocn > 0) { *cm = ocm; *cn = ocn; }
-}
-// env DVD_TC_PAIR=0 disables the CTA-pair (cta_group::2) kernels
-static bool pair_enabled() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("DVD_TC_PAIR");
-    v = (e && e[0] == '0') ? 0 : 1;
-  }
-  return v != 0;
-}
-static void pick_cluster(int mt, int nt, int nsm, int* cm, int* cn) {
-  int want_m = 1, want_n = 1;      // measured: multicast alone does not pay (the SM-side ingest is the limit)
-  cluster_override(&want_m, &want_n);
-  int m = 1, n = 1;
-  while (m * 2 <= want_m && mt % (m * 2) == 0) m *= 2;
-  while (n * 2 <= want_n && nt % (n * 2) == 0) n *= 2;
-  if (n < want_n && want_m * want_n >= 4)          // n-tiles do not divide: take the sharing along M instead
-    while (m * 2 <= 4 && m * n * 2 <= want_m * want_n && mt % (m * 2) == 0) m *= 2;
-  if ((int64_t)mt * nt < nsm) { m = 1; n = 1; }    // under one wave: keep every SM busy instead
-  *cm = m; *cn = n;
-}
 
 }  // namespace tma
 
-// env DVD_CONV_IMPL: "simt" = fp32 FFMA only, "tc" = register-staged tcgen05 (v1), default = TMA tcgen05
-static int impl_pref2() {
-  static int pref = -1;
-  if (pref < 0) {
-    const char* e = getenv("DVD_CONV_IMPL");
-    pref = (e && strcmp(e, "simt") == 0) ? 0 : ((e && strcmp(e, "tc") == 0) ? 1 : 2);
-  }
-  return pref;
-}
-
 bool tma_fwd_eligible(const ConvP& p) {
-  if (impl_pref2() != 2) return false;
+  if (get_option(OPT_SIMT_ONLY)) return false;
   const dvd_conv_desc& d = p.d;
   // narrow layers (3-channel image convs) ride the tensor path, zero-padded to one 64-wide block, once there are
   // enough pixels for the padding not to matter: the SIMT engine runs them at < 1 TFLOP/s
@@ -1270,17 +1041,16 @@ bool tma_fwd_eligible(const ConvP& p) {
 
 int tma_fwd_launch(ConvP& p, cudaStream_t st) { return tma_fwd_launch_ex(p, nullptr, nullptr, st); }
 bool tma_fwd_launch_ex_eligible(const ConvP& p) { return tma_fwd_eligible(p); }
-bool tma_forward_planes_fp16() { return tma::lo_fp16_enabled(); }
 
-int tma_split_weights(const float* w_packed, int taps, int Cin, int Cout, int CoutP, int fp16, void* hi, void* lo,
+int tma_split_weights(const float* w_packed, int taps, int Cin, int Cout, int CoutP, void* hi, void* lo,
                       cudaStream_t st) {
   // [tap][Cin][Cout] fp32 -> [tap][CoutP][CinP]   (image = tap, channel = cin, pixel = cout)
   return tma::prep_planes(w_packed, taps, 1, Cin, tma_round64(Cin), (int64_t)Cin * Cout, 0, Cout, Cout, CoutP, 1, 1, 0,
-                          0, fp16, reinterpret_cast<__nv_bfloat16*>(hi), reinterpret_cast<__nv_bfloat16*>(lo), st);
+                          0, reinterpret_cast<__nv_bfloat16*>(hi), reinterpret_cast<__nv_bfloat16*>(lo), st);
 }
-int tma_split_activations(const float* x, int N, int C, int64_t n_stride, int64_t c_stride, int pix, int fp16, void* hi,
-                          void* lo, cudaStream_t st) {
-  return tma::prep_planes(x, N, 1, C, tma_round64(C), n_stride, 0, c_stride, pix, pix, 1, 1, 0, 0, fp16,
+int tma_split_activations(const float* x, int N, int C, int64_t n_stride, int64_t c_stride, int pix, void* hi, void* lo,
+                          cudaStream_t st) {
+  return tma::prep_planes(x, N, 1, C, tma_round64(C), n_stride, 0, c_stride, pix, pix, 1, 1, 0, 0,
                           reinterpret_cast<__nv_bfloat16*>(hi), reinterpret_cast<__nv_bfloat16*>(lo), st);
 }
 
@@ -1294,24 +1064,18 @@ int tma_fwd_launch_ex(ConvP& p, const TmaOperands* ops, const GruEpi* epi, cudaS
   const int CinP = round_up(d.Cin, 64);
   p.ck = CinP / 64;
   p.iters_total = p.taps * p.ck;
-  const int pmode = promote_mode();
-  int bn = pick_bn(d.Cout, pmode == 1 ? 128 : 256, true);
+  int bn = pick_bn(d.Cout, true);
   const int mt = ceil_div(p.M, BM);
   if (bn > 128 && (int64_t)mt * ceil_div(d.Cout, bn) < nsm) bn = 128;        // small grids: more, narrower tiles
   // short reductions prefer 128-wide tiles with two CTAs per SM over one 256-wide tile (+7 % on the 3x3 convs at
-  // 256 channels; env DVD_TC_SHORTK_BN128=0 turns it off)
-  static const bool shortk128 = [] { const char* e = getenv("DVD_TC_SHORTK_BN128"); return !(e && e[0] == '0'); }();
-  if (shortk128 && bn > 128 && p.iters_total <= 40 && d.Cout % 128 == 0 && !(epi && epi->mode)) bn = 128;
-  const bool promote = pmode != 0 && bn <= 128 && p.iters_total > PROMOTE_MIN;
+  // 256 channels)
+  if (bn > 128 && p.iters_total <= 40 && d.Cout % 128 == 0 && !(epi && epi->mode)) bn = 128;
   const bool ext_w = ops && ops->w_hi, ext_a = ops && ops->a_hi;
   const int CoutP = ext_w ? ops->CoutP : round_up(d.Cout, bn);
   fp.CoutP = CoutP;
   if (epi) fp.gru = *epi;
-  static const int epi_prefetch = [] { const char* e = getenv("DVD_TC_EPI_PREFETCH"); return (e && e[0] == '0') ? 0 : 1; }();
-  fp.prefetch = epi_prefetch;
+  fp.prefetch = get_option(OPT_EPI_PREFETCH);
   if (fp.gru.mode) DVD_CHECK_ARG(d.accumulate && fp.gru.Ch % 32 == 0 && !d.out_act && !p.res && !p.bias);
-  fp.fp16 = (lo_fp16_enabled() && d.x_kind == 1) ? 1 : 0;
-  fp.lo_inv = fp.fp16 ? 1.f / kLoScaleFp16 : 1.f / kLoScaleBf16;
   const int64_t ctas = (int64_t)mt * ceil_div(d.Cout, bn);
   int nsplit = 1;
   if (ctas < nsm && d.out_act == 0 && p.iters_total >= 8 && !fp.gru.mode) {
@@ -1343,7 +1107,7 @@ int tma_fwd_launch_ex(ConvP& p, const TmaOperands* ops, const GruEpi* epi, cudaS
   } else {
     __nv_bfloat16* h = cur; __nv_bfloat16* l = cur + a_elems; cur += 2 * a_elems;
     DVD_TRY(prep_planes(p.x, d.N1, d.N2, d.Cin, CinP, d.x_s1, d.x_s2, d.x_cs, p.DHW, p.DHW, d.W, p.HW, d.in_up,
-                        d.in_relu, fp.fp16, h, l, st));
+                        d.in_relu, h, l, st));
     a_hi = h; a_lo = l;
   }
   if (ext_w) {
@@ -1353,66 +1117,55 @@ int tma_fwd_launch_ex(ConvP& p, const TmaOperands* ops, const GruEpi* epi, cudaS
     __nv_bfloat16* h = cur; __nv_bfloat16* l = cur + w_elems;
     // weights: [tap][Cin][Cout] fp32 -> [tap][CoutP][CinP]   (image = tap, channel = cin, pixel = cout)
     DVD_TRY(prep_planes(p.w, p.taps, 1, d.Cin, CinP, (int64_t)d.Cin * d.Cout, 0, d.Cout, d.Cout, CoutP, 1, 1, 0, 0,
-                        fp.fp16, h, l, st));
+                        h, l, st));
     w_hi = h; w_lo = l;
   }
   CUtensorMap maps[4];
-  // CTA pairs (256 x bn tiles) whenever there is more than one wave of tiles; otherwise optional multicast clusters,
-  // only where the slices are still legal TMA boxes
-  const bool pair = pair_enabled() && mt % 2 == 0 && ctas >= nsm && bn >= 64;
-  fp.cm = fp.cn = 1;
-  if (!pair) pick_cluster(mt, ceil_div(d.Cout, bn), nsm, &fp.cm, &fp.cn);
-  TileGeom ga = fp.g;
-  while (fp.cn > 1 && !tile_geom(BM / fp.cn, N, d.D, d.H, d.W, &ga)) fp.cn >>= 1;
-  if (fp.cn == 1) ga = fp.g;
+  // CTA pairs (256 x bn tiles) whenever there is more than one wave of tiles
+  const bool pair = get_option(OPT_PAIR) && mt % 2 == 0 && ctas >= nsm && bn >= 64;
   const int a_Cp = (ext_a && ops->a_Cp) ? ops->a_Cp : CinP;
   const int64_t a_stride = ext_a ? ops->a_img_stride : 0;
   fp.a_c_off = ext_a ? ops->a_c_off : 0;
   if (ext_a) DVD_CHECK_ARG(a_Cp % 64 == 0 && fp.a_c_off % 64 == 0 && fp.a_c_off + CinP <= a_Cp);
-  DVD_TRY(make_act_map(&maps[0], a_hi, N, d.D, d.H, d.W, a_Cp, ga, a_stride));
-  DVD_TRY(make_act_map(&maps[1], a_lo, N, d.D, d.H, d.W, a_Cp, ga, a_stride));
-  DVD_TRY(make_w_map(&maps[2], w_hi, p.taps * CoutP, CinP, pair ? bn / 2 : bn / fp.cm));
-  DVD_TRY(make_w_map(&maps[3], w_lo, p.taps * CoutP, CinP, pair ? bn / 2 : bn / fp.cm));
+  DVD_TRY(make_act_map(&maps[0], a_hi, N, d.D, d.H, d.W, a_Cp, fp.g, a_stride));
+  DVD_TRY(make_act_map(&maps[1], a_lo, N, d.D, d.H, d.W, a_Cp, fp.g, a_stride));
+  DVD_TRY(make_w_map(&maps[2], w_hi, p.taps * CoutP, CinP, pair ? bn / 2 : bn));
+  DVD_TRY(make_w_map(&maps[3], w_lo, p.taps * CoutP, CinP, pair ? bn / 2 : bn));
   fp.c = p;
   dim3 grid(mt, ceil_div(d.Cout, bn), nsplit);
+  // persistent CTA pairs when there is more than one wave of tiles
+  fp.nt = ceil_div(d.Cout, bn);
+  fp.tiles = (mt / (pair ? 2 : 1)) * fp.nt;
+  const bool persist = get_option(OPT_PERSIST) && pair && nsplit == 1 && bn >= 128 && fp.tiles > nsm / 2;
+  const bool oneacc = persist && get_option(OPT_ONEACC);
+  // short reductions on narrow tiles: two CTAs per SM
+  const bool occ2 = get_option(OPT_OCC2) && !fp.gru.mode && bn <= 128 && p.iters_total <= 40 &&
+                    ctas >= 2 * (int64_t)nsm && (pair || bn == 64);     // (one CTA, 128 wide) stages are 64 KB: no room
   prof_tag(pair ? "fwd M%d Ci%d Co%d t%d bn%d pair acc%d" : "fwd M%d Ci%d Co%d t%d bn%d acc%d", p.M, d.Cin, d.Cout,
            p.taps, bn, d.accumulate + 2 * (nsplit > 1) + 4 * (fp.gru.mode != 0));
   prof_begin(0, 2.0 * p.M * (double)d.Cout * d.Cin * p.taps, st);
   int rc;
-  // short reductions on narrow tiles: two CTAs per SM (env DVD_TC_OCC2=0 turns it off)
-  // persistent CTA pairs when there is more than one wave of tiles (env DVD_TC_PERSIST=0 turns it off)
-  static const bool persist_on = [] { const char* e = getenv("DVD_TC_PERSIST"); return !(e && e[0] == '0'); }();
-  fp.nt = ceil_div(d.Cout, bn);
-  fp.tiles = (mt / (pair ? 2 : 1)) * fp.nt;
-  const bool persist = persist_on && pair && !promote && nsplit == 1 && fp.cm * fp.cn == 1 &&
-                       fp.tiles > nsm / 2;
-  static const bool ew8 = [] { const char* e = getenv("DVD_TC_EW8"); return !(e && e[0] == '0'); }();
-  static const bool ew8b = [] { const char* e = getenv("DVD_TC_EW8B"); return !(e && e[0] == '0'); }();
-  static const int occ2_iters = [] { const char* e = getenv("DVD_TC_OCC2_ITERS"); return e ? atoi(e) : 40; }();
-  static const bool occ2_on = [] { const char* e = getenv("DVD_TC_OCC2"); return !(e && e[0] == '0'); }();
-  const bool occ2 = occ2_on && !promote && !fp.gru.mode && bn <= 128 && p.iters_total <= occ2_iters &&
-                    ctas >= 2 * (int64_t)nsm && (pair || bn == 64);     // (one CTA, 128 wide) stages are 64 KB: no room
   if (occ2) {
-    if (pair) rc = bn == 128 ? launch_fwd<128, false, 2, 2>(maps, fp, grid, st) : launch_fwd<64, false, 2, 2>(maps, fp, grid, st);
-    else rc = launch_fwd<64, false, 1, 2>(maps, fp, grid, st);
-  } else if (persist && pair && bn >= 128) {      // persistent CTA pairs, 8 epilogue warps
-    if (bn == 256) rc = launch_fwd<256, false, 2, 1, 8, true>(maps, fp, grid, st);
-    else if (bn == 192) rc = launch_fwd<192, false, 2, 1, 8, true>(maps, fp, grid, st);
-    else rc = launch_fwd<128, false, 2, 1, 8, true>(maps, fp, grid, st);
-  } else if (pair && ew8 && bn >= 192) {
-    rc = bn == 256 ? launch_fwd<256, false, 2, 1, 8>(maps, fp, grid, st) : launch_fwd<192, false, 2, 1, 8>(maps, fp, grid, st);
-  } else if (ew8b && !promote && bn == 128) {     // 8 epilogue warps on the 128-wide tiles too (+0.4 %)
-    rc = pair ? launch_fwd<128, false, 2, 1, 8>(maps, fp, grid, st) : launch_fwd<128, false, 1, 1, 8>(maps, fp, grid, st);
+    if (pair) rc = bn == 128 ? launch_fwd<128, 2, 2>(maps, fp, grid, st) : launch_fwd<64, 2, 2>(maps, fp, grid, st);
+    else rc = launch_fwd<64, 1, 2>(maps, fp, grid, st);
+  } else if (persist && oneacc) {           // two accumulator sets: the epilogue is hidden under the next tile
+    if (bn == 256) rc = launch_fwd<256, 2, 1, 8, true, true>(maps, fp, grid, st);
+    else if (bn == 192) rc = launch_fwd<192, 2, 1, 8, true, true>(maps, fp, grid, st);
+    else rc = launch_fwd<128, 2, 1, 8, true, true>(maps, fp, grid, st);
+  } else if (persist) {                     // persistent CTA pairs, 8 epilogue warps
+    if (bn == 256) rc = launch_fwd<256, 2, 1, 8, true>(maps, fp, grid, st);
+    else if (bn == 192) rc = launch_fwd<192, 2, 1, 8, true>(maps, fp, grid, st);
+    else rc = launch_fwd<128, 2, 1, 8, true>(maps, fp, grid, st);
   } else if (pair) {
-    if (bn == 256) rc = launch_fwd<256, false, 2>(maps, fp, grid, st);
-    else if (bn == 192) rc = launch_fwd<192, false, 2>(maps, fp, grid, st);
-    else if (bn == 128) rc = promote ? launch_fwd<128, true, 2>(maps, fp, grid, st) : launch_fwd<128, false, 2>(maps, fp, grid, st);
-    else rc = promote ? launch_fwd<64, true, 2>(maps, fp, grid, st) : launch_fwd<64, false, 2>(maps, fp, grid, st);
+    if (bn == 256) rc = launch_fwd<256, 2, 1, 8>(maps, fp, grid, st);
+    else if (bn == 192) rc = launch_fwd<192, 2, 1, 8>(maps, fp, grid, st);
+    else if (bn == 128) rc = launch_fwd<128, 2, 1, 8>(maps, fp, grid, st);
+    else rc = launch_fwd<64, 2>(maps, fp, grid, st);
   } else {
-    if (bn == 256) rc = launch_fwd<256, false, 1>(maps, fp, grid, st);
-    else if (bn == 192) rc = launch_fwd<192, false, 1>(maps, fp, grid, st);
-    else if (bn == 128) rc = promote ? launch_fwd<128, true, 1>(maps, fp, grid, st) : launch_fwd<128, false, 1>(maps, fp, grid, st);
-    else rc = promote ? launch_fwd<64, true, 1>(maps, fp, grid, st) : launch_fwd<64, false, 1>(maps, fp, grid, st);
+    if (bn == 256) rc = launch_fwd<256, 1>(maps, fp, grid, st);
+    else if (bn == 192) rc = launch_fwd<192, 1>(maps, fp, grid, st);
+    else if (bn == 128) rc = launch_fwd<128, 1, 1, 8>(maps, fp, grid, st);
+    else rc = launch_fwd<64, 1>(maps, fp, grid, st);
   }
   prof_end(0, st);
   if (rc) return rc;
@@ -1421,7 +1174,7 @@ int tma_fwd_launch_ex(ConvP& p, const TmaOperands* ops, const GruEpi* epi, cudaS
 }
 
 bool tma_wgrad_eligible(const ConvP& p) {
-  if (impl_pref2() != 2) return false;
+  if (get_option(OPT_SIMT_ONLY)) return false;
   const dvd_conv_desc& d = p.d;
   if (p.M < 4096 || d.in_up || ((d.Cin < 32 || d.Cout < 64) && p.M < (1 << 18))) return false;
   if ((int64_t)d.N1 * d.N2 > 65535) return false;
@@ -1442,8 +1195,7 @@ void tma_scratch_free(void* p, cudaStream_t st) {
 }
 int tma_split_gradients(const float* g, int N, int C, int64_t n_stride, int64_t c_stride, int pix, void* hi, void* lo,
                         cudaStream_t st) {
-  return tma::prep_planes(g, N, 1, C, tma_round64(C), n_stride, 0, c_stride, pix, pix, 1, 1, 0, 0, 0,
-                          reinterpret_cast<__nv_bfloat16*>(hi), reinterpret_cast<__nv_bfloat16*>(lo), st);
+  return tma_split_activations(g, N, C, n_stride, c_stride, pix, hi, lo, st);
 }
 int tma_wgrad_launch(ConvP& p, float* dwp, cudaStream_t st) { return tma_wgrad_launch_ex(p, dwp, nullptr, st); }
 // shared dY planes need whole images per 64-pixel box unless they map one to one
@@ -1461,10 +1213,8 @@ int tma_wgrad_launch_ex(ConvP& p, float* dwp, const TmaWgOperands* ops, cudaStre
   const int N = d.N1 * d.N2;
   WgP wp;
   if (!tile_geom(64, N, d.D, d.H, d.W, &wp.g)) return fail("internal: geometry%s (%s:%d)", "", __FILE__, __LINE__);
-  const int pmode = promote_mode();
-  const int bn = pick_bn(d.Cout, pmode == 1 ? 128 : 256, false);
-  const bool promote = pmode != 0 && bn <= 128;  // k = pixels: every CTA runs hundreds of k-blocks
-  const bool pair = pair_enabled() && d.Cin % 256 == 0 && bn >= 128;
+  const int bn = pick_bn(d.Cout, false);
+  const bool pair = get_option(OPT_PAIR) && d.Cin % 256 == 0 && bn >= 128;
   const int64_t base = (int64_t)ceil_div(d.Cin, BM) * ceil_div(d.Cout, bn) * p.taps;
   // split the pixel range: cost model = waves of CTAs x (k-blocks per CTA + a fixed per-CTA cost of ~40 k-blocks for
   // the prologue and the atomic epilogue); whole waves matter for the long reductions (M = millions of pixels), the
@@ -1497,7 +1247,7 @@ int tma_wgrad_launch_ex(ConvP& p, float* dwp, const TmaWgOperands* ops, cudaStre
   __nv_bfloat16* x_lo = x_hi + x_elems;
   const __nv_bfloat16 *y_hi, *y_lo;
   DVD_TRY(prep_planes(p.x, d.N1, d.N2, d.Cin, CinP, d.x_s1, d.x_s2, d.x_cs, p.DHW, p.DHW, d.W, p.HW, 0, d.in_relu,
-                      0, x_hi, x_lo, st));
+                      x_hi, x_lo, st));
   int y_images = N;
   wp.y_c_off = 0; wp.y_T = 0; wp.y_t_off = 0; wp.y_n2 = d.N2;
   if (ext_y) {
@@ -1508,7 +1258,7 @@ int tma_wgrad_launch_ex(ConvP& p, float* dwp, const TmaWgOperands* ops, cudaStre
     if (!(ops->y_T == d.N2 && ops->y_t_off == 0)) { wp.y_T = ops->y_T; wp.y_t_off = ops->y_t_off; }
   } else {
     __nv_bfloat16* h = x_lo + x_elems; __nv_bfloat16* l = h + y_elems;
-    DVD_TRY(prep_planes(p.y, d.N1, d.N2, d.Cout, CoutP, d.y_s1, d.y_s2, d.y_cs, p.DHW, p.DHW, d.W, p.HW, 0, 0, 0, h, l, st));
+    DVD_TRY(prep_planes(p.y, d.N1, d.N2, d.Cout, CoutP, d.y_s1, d.y_s2, d.y_cs, p.DHW, p.DHW, d.W, p.HW, 0, 0, h, l, st));
     y_hi = h; y_lo = l;
   }
   CUtensorMap maps[4];
@@ -1517,30 +1267,17 @@ int tma_wgrad_launch_ex(ConvP& p, float* dwp, const TmaWgOperands* ops, cudaStre
   DVD_TRY(make_act_map(&maps[2], y_hi, y_images, d.D, d.H, d.W, CoutP, wp.g));
   DVD_TRY(make_act_map(&maps[3], y_lo, y_images, d.D, d.H, d.W, CoutP, wp.g));
   wp.c = p;
-  {
-    // cluster over (ci-blocks, co-blocks): cm shares the dY tile, cn the X tile
-    const int cib = ceil_div(d.Cin, BM), cob = ceil_div(d.Cout, bn);
-    int want_m = 1, want_n = 1;
-    cluster_override(&want_m, &want_n);
-    wp.cm = (want_m >= 2 && cib % 2 == 0 && bn >= 128) ? 2 : 1;
-    wp.cn = (want_n >= 2 && cob % 2 == 0) ? 2 : 1;
-    if (pair) wp.cm = wp.cn = 1;
-  }
   dim3 grid(ceil_div(d.Cin, BM), ceil_div(d.Cout, bn), p.taps * nsplit);
   prof_tag(pair ? "wgrad M%d Ci%d Co%d t%d bn%d pair ns%d" : "wgrad M%d Ci%d Co%d t%d bn%d ns%d", p.M, d.Cin, d.Cout,
            p.taps, bn, nsplit);
   prof_begin(1, 2.0 * p.M * (double)d.Cout * d.Cin * p.taps, st);
   int rc;
   if (pair) {
-    if (bn == 256) rc = launch_wgrad<256, false, 2>(maps, wp, dwp, grid, st);
-    else rc = promote ? launch_wgrad<128, true, 2>(maps, wp, dwp, grid, st)
-                      : launch_wgrad<128, false, 2>(maps, wp, dwp, grid, st);
+    rc = bn == 256 ? launch_wgrad<256, 2>(maps, wp, dwp, grid, st) : launch_wgrad<128, 2>(maps, wp, dwp, grid, st);
   } else {
-    if (bn == 256) rc = launch_wgrad<256, false, 1>(maps, wp, dwp, grid, st);
-    else if (bn == 128) rc = promote ? launch_wgrad<128, true, 1>(maps, wp, dwp, grid, st)
-                                     : launch_wgrad<128, false, 1>(maps, wp, dwp, grid, st);
-    else rc = promote ? launch_wgrad<64, true, 1>(maps, wp, dwp, grid, st)
-                      : launch_wgrad<64, false, 1>(maps, wp, dwp, grid, st);
+    if (bn == 256) rc = launch_wgrad<256, 1>(maps, wp, dwp, grid, st);
+    else if (bn == 128) rc = launch_wgrad<128, 1>(maps, wp, dwp, grid, st);
+    else rc = launch_wgrad<64, 1>(maps, wp, dwp, grid, st);
   }
   prof_end(1, st);
   if (rc) return rc;

@@ -6,7 +6,6 @@
 // overwritten in place with the pre-activation gradients, which then feed ONE batched x-dgrad and the batched
 // weight gradients.
 #include <cuda_bf16.h>
-#include <cuda_fp16.h>
 
 #include "common.cuh"
 #include "conv_params.cuh"
@@ -87,7 +86,7 @@ __global__ void gru_bwd2_kernel(float* __restrict__ g_t, int64_t g_bs, const flo
   }
 }
 
-// ---- backward kernels that ALSO write the bf16 (hi, lo * 2^8) operand planes of the pre-activation gradients.
+// ---- backward kernels that ALSO write the bf16 (hi, lo) operand planes of the pre-activation gradients.
 // Planes: [B*T][HW][G3P] channels-last, channel order (da_u | da_r | da_o) = the layer's gate order; they are read
 // by the two per-step dgrad GEMMs, the batched x-dgrad and the three weight-gradient GEMMs, so the gradients are
 // split exactly once, by the kernel that produces them.  Block = 32 pixels x 64 channels of one image, transposed
@@ -98,7 +97,7 @@ __device__ __forceinline__ void bf16_split8(const float* v, uint4* hi, uint4* lo
   for (int i = 0; i < 4; ++i) {
     const __nv_bfloat162 hp = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
     const float2 hf = __bfloat1622float2(hp);
-    const __nv_bfloat162 lp = __floats2bfloat162_rn((v[2 * i] - hf.x) * 256.f, (v[2 * i + 1] - hf.y) * 256.f);
+    const __nv_bfloat162 lp = __floats2bfloat162_rn(v[2 * i] - hf.x, v[2 * i + 1] - hf.y);
     h[i] = *reinterpret_cast<const uint32_t*>(&hp);
     l[i] = *reinterpret_cast<const uint32_t*>(&lp);
   }
@@ -207,7 +206,7 @@ struct GruWs {
   float *dwx, *dwhur, *dwho;            // packed weight grads
   float *d_rh, *carry0, *carry1, *dbias;
   double* dscratch;
-  // fused forward path: fp16 hi/lo planes of the h-half weights and of the per-step GEMM inputs
+  // fused forward path: bf16 hi/lo planes of the h-half weights and of the per-step GEMM inputs
   uint16_t *whur_hi, *whur_lo, *who_hi, *who_lo;      // [taps][CoutP][ChP]
   uint16_t *hpl_hi[2], *hpl_lo[2];                    // planes of h_{t-1} / h_t (ping-pong), [B*HW][ChP]
   uint16_t *rhpl_hi, *rhpl_lo;                        // planes of r * h_{t-1}
@@ -255,15 +254,8 @@ static GruWs carve(void* base, int B, int Cx, int Ch, int HW, int taps, bool bwd
   return w;
 }
 
-// env DVD_GRU_FUSED=0: keep the gate math in separate elementwise kernels
-static bool gru_fused_enabled() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("DVD_GRU_FUSED");
-    v = (e && e[0] == '0') ? 0 : 1;
-  }
-  return v != 0;
-}
+// option "gru_fused" = 0: keep the gate math in separate elementwise kernels
+static bool gru_fused_enabled() { return get_option(OPT_GRU_FUSED) != 0; }
 
 static dvd_conv_desc base_desc(int B, int T, int Cin, int Cout, int H, int W, int k) {
   dvd_conv_desc d;
@@ -310,17 +302,17 @@ extern "C" int dvd_convgru_layer_fwd(const float* x, int64_t x_bs, int64_t x_ts,
   }
   const int eb = ew_blocks((int64_t)B * chw);
   // Fused path: the two h-half GEMMs of a step run on the TMA/tcgen05 engine with the gate math in their epilogues
-  // (update|reset: sigmoid, r*h;  out: tanh, state update) which also emit the fp16 planes the next GEMM reads, and the
+  // (update|reset: sigmoid, r*h;  out: tanh, state update) which also emit the bf16 planes the next GEMM reads, and the
   // h-half weight planes are split once per layer instead of once per step.
   dvd_conv_desc d_ur = base_desc(B, 1, Ch, 2 * Ch, H, W, k), d_o = base_desc(B, 1, Ch, Ch, H, W, k);
   d_ur.x_kind = d_o.x_kind = 1; d_ur.accumulate = d_o.accumulate = 1;
   d_ur.y_s1 = d_o.y_s1 = g_bs; d_ur.x_s1 = d_o.x_s1 = chw;
   const int ChP = tma_round64(Ch), Co2P = tma_round64(2 * Ch);
-  const bool fused = gru_fused_enabled() && T > 1 && Ch % 32 == 0 && tma_forward_planes_fp16() &&
-                     conv_fwd_ex_eligible(&d_ur) && conv_fwd_ex_eligible(&d_o);
+  const bool fused = gru_fused_enabled() && T > 1 && Ch % 32 == 0 && conv_fwd_ex_eligible(&d_ur) &&
+                     conv_fwd_ex_eligible(&d_o);
   if (fused) {
-    DVD_TRY(tma_split_weights(ws.whur, taps, Ch, 2 * Ch, Co2P, 1, ws.whur_hi, ws.whur_lo, st));
-    DVD_TRY(tma_split_weights(ws.who, taps, Ch, Ch, ChP, 1, ws.who_hi, ws.who_lo, st));
+    DVD_TRY(tma_split_weights(ws.whur, taps, Ch, 2 * Ch, Co2P, ws.whur_hi, ws.whur_lo, st));
+    DVD_TRY(tma_split_weights(ws.who, taps, Ch, Ch, ChP, ws.who_hi, ws.who_lo, st));
     if (ChP != Ch) {      // padded channels of the planes the epilogues write stay zero
       const size_t pl = (size_t)B * HW * ChP * sizeof(uint16_t);
       for (int i = 0; i < 2; ++i) {
@@ -340,7 +332,7 @@ extern "C" int dvd_convgru_layer_fwd(const float* x, int64_t x_bs, int64_t x_ts,
     if (fused && hp) {
       const int sp = (t + 1) & 1, sn = t & 1;          // slots of h_{t-1} and h_t
       if (!have_planes)
-        DVD_TRY(tma_split_activations(hp, B, Ch, hp_bs, HW, HW, 1, ws.hpl_hi[sp], ws.hpl_lo[sp], st));
+        DVD_TRY(tma_split_activations(hp, B, Ch, hp_bs, HW, HW, ws.hpl_hi[sp], ws.hpl_lo[sp], st));
       TmaOperands op;
       GruEpi ge;
       op.a_hi = ws.hpl_hi[sp]; op.a_lo = ws.hpl_lo[sp]; op.w_hi = ws.whur_hi; op.w_lo = ws.whur_lo; op.CoutP = Co2P;
@@ -405,8 +397,8 @@ extern "C" int dvd_convgru_layer_bwd(const float* x, int64_t x_bs, int64_t x_ts,
   const int ChP = tma_round64(Ch), Co2P = tma_round64(2 * Ch);
   const bool wplanes = gru_fused_enabled() && T > 1 && conv_fwd_ex_eligible(&d_rh) && conv_fwd_ex_eligible(&d_hp);
   if (wplanes) {
-    DVD_TRY(tma_split_weights(ws.whoT, taps, Ch, Ch, ChP, 0, ws.whoT_hi, ws.whoT_lo, st));
-    DVD_TRY(tma_split_weights(ws.whurT, taps, 2 * Ch, Ch, ChP, 0, ws.whurT_hi, ws.whurT_lo, st));
+    DVD_TRY(tma_split_weights(ws.whoT, taps, Ch, Ch, ChP, ws.whoT_hi, ws.whoT_lo, st));
+    DVD_TRY(tma_split_weights(ws.whurT, taps, 2 * Ch, Ch, ChP, ws.whurT_hi, ws.whurT_lo, st));
   }
   // The pre-activation gradients (da_u | da_r | da_o) of all frames feed four GEMMs (x-dgrad and the three weight
   // gradients): split them into bf16 planes ONCE and hand the planes to all four (channel / frame offsets in the
@@ -422,7 +414,7 @@ extern "C" int dvd_convgru_layer_bwd(const float* x, int64_t x_bs, int64_t x_ts,
   d_dx.x_s1 = g_bs; d_dx.x_s2 = g_ts; d_dx.y_s1 = (int64_t)T * Cx * HW; d_dx.y_s2 = (int64_t)Cx * HW;
   dvd_conv_desc d_wx = base_desc(B, T, Cx, 3 * Ch, H, W, k); d_wx.x_kind = 1;
   d_wx.x_s1 = x_bs; d_wx.x_s2 = x_ts; d_wx.y_s1 = g_bs; d_wx.y_s2 = g_ts;
-  static const bool share_on = [] { const char* e = getenv("DVD_GRU_SHARE_PLANES"); return !(e && e[0] == '0'); }();
+  const bool share_on = get_option(OPT_GRU_SHARE_PLANES) != 0;
   yo.y_Cp = G3P; yo.y_T = T;
   bool share = share_on && Ch % 32 == 0 && conv_fwd_ex_eligible(&d_dx);
   if (share) {
@@ -432,7 +424,7 @@ extern "C" int dvd_convgru_layer_bwd(const float* x, int64_t x_bs, int64_t x_ts,
   }
   // gplanes: the BPTT kernels write the planes themselves (frame by frame) and the per-step dgrad GEMMs read their
   // A operand from them too; otherwise the planes are split from the fp32 buffer after the sweep
-  static const bool gplanes_on = [] { const char* e = getenv("DVD_GRU_BWD_PLANES"); return !(e && e[0] == '0'); }();
+  const bool gplanes_on = get_option(OPT_GRU_BWD_PLANES) != 0;
   const bool gplanes = gplanes_on && share && wplanes && Ch % 64 == 0;
   __nv_bfloat16 *pl_hi = nullptr, *pl_lo = nullptr;
   const int64_t pl_frame = (int64_t)HW * G3P, pl_img = (int64_t)T * pl_frame;

@@ -365,18 +365,29 @@ __global__ void gather_flat_kernel(const GatherP gp, float* __restrict__ flat) {
 __global__ void axpby_kernel(const float* __restrict__ x, float a, float b, int64_t n, float* __restrict__ y) {
   GRID_STRIDE(i, n) y[i] = b == 0.f ? a * __ldg(x + i) : fmaf(a, __ldg(x + i), b * y[i]);
 }
+// Class ids index embedding tables (nn.Embedding raises on an id outside [0, rows); a raw pointer cannot): an
+// out-of-range id is counted in g_index_errors (dvd_index_errors reads it) and clamped so no access leaves the table.
+__device__ unsigned int g_index_errors = 0;
+__device__ __forceinline__ int64_t checked_index(int64_t i, int rows, bool count) {
+  if (i < 0 || i >= rows) {
+    if (count) atomicAdd(&g_index_errors, 1u);
+    return i < 0 ? 0 : rows - 1;
+  }
+  return i;
+}
+
 __global__ void embedding_fwd_kernel(const float* __restrict__ w, const int64_t* __restrict__ idx, int n, int dim,
-                                     float* __restrict__ y) {
+                                     int rows, float* __restrict__ y) {
   GRID_STRIDE(i, (int64_t)n * dim) {
     const int r = (int)(i / dim), c = (int)(i % dim);
-    y[i] = __ldg(w + idx[r] * dim + c);
+    y[i] = __ldg(w + checked_index(idx[r], rows, c == 0) * dim + c);       // one count per looked-up row
   }
 }
 __global__ void embedding_bwd_kernel(const float* __restrict__ dy, const int64_t* __restrict__ idx, int n, int dim,
-                                     float* __restrict__ dw) {
+                                     int rows, float* __restrict__ dw) {
   GRID_STRIDE(i, (int64_t)n * dim) {
     const int r = (int)(i / dim), c = (int)(i % dim);
-    atomicAdd(dw + idx[r] * dim + c, __ldg(dy + i));
+    atomicAdd(dw + checked_index(idx[r], rows, false) * dim + c, __ldg(dy + i));       // counted by the forward
   }
 }
 
@@ -384,11 +395,17 @@ __global__ void embedding_bwd_kernel(const float* __restrict__ dy, const int64_t
 __global__ void dhead_fwd_kernel(const float* __restrict__ x, int C, int HW, int T, const float* __restrict__ wl,
                                  const float* __restrict__ sl, const float* __restrict__ bl,
                                  const float* __restrict__ emb, const float* __restrict__ se,
-                                 const int64_t* __restrict__ cls, float* __restrict__ feat, float* __restrict__ out) {
+                                 const int64_t* __restrict__ cls, int n_class, float* __restrict__ feat,
+                                 float* __restrict__ out) {
   __shared__ float red[32];
   const int n = blockIdx.x;
   const float isl = 1.f / __ldg(sl), ise = 1.f / __ldg(se);
-  const float* e = emb + cls[n / T] * C;
+  int64_t cl = cls[n / T];
+  if (cl < 0 || cl >= n_class) {          // one count per frame, not per thread
+    if (threadIdx.x == 0) atomicAdd(&g_index_errors, 1u);
+    cl = cl < 0 ? 0 : n_class - 1;
+  }
+  const float* e = emb + cl * C;
   float acc = 0.f;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const float* p = x + ((int64_t)n * C + c) * HW;
@@ -404,11 +421,13 @@ __global__ void dhead_fwd_kernel(const float* __restrict__ x, int C, int HW, int
 __global__ void dhead_bwd_kernel(const float* __restrict__ x, const float* __restrict__ feat,
                                  const float* __restrict__ dout, int C, int HW, int T, const float* __restrict__ wl,
                                  const float* __restrict__ sl, const float* __restrict__ emb,
-                                 const float* __restrict__ se, const int64_t* __restrict__ cls, float* __restrict__ dx,
-                                 float* __restrict__ dwl, float* __restrict__ db, float* __restrict__ demb) {
+                                 const float* __restrict__ se, const int64_t* __restrict__ cls, int n_class,
+                                 float* __restrict__ dx, float* __restrict__ dwl, float* __restrict__ db,
+                                 float* __restrict__ demb) {
   const int n = blockIdx.x;
   const float isl = 1.f / __ldg(sl), ise = 1.f / __ldg(se);
-  const int64_t cl = cls[n / T];
+  int64_t cl = cls[n / T];
+  if (cl < 0 || cl >= n_class) cl = cl < 0 ? 0 : n_class - 1;      // counted by the forward
   const float* e = emb + cl * C;
   const float g = __ldg(dout + n);
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -665,28 +684,30 @@ extern "C" int dvd_axpby(const float* x, float a, float b, int64_t n, float* y, 
   DVD_LAUNCH_CHECK();
   return 0;
 }
-extern "C" int dvd_embedding_fwd(const float* w, const int64_t* idx, int n, int dim, float* y, void* stream) {
+extern "C" int dvd_embedding_fwd(const float* w, const int64_t* idx, int n, int dim, int rows, float* y,
+                                 void* stream) {
   dvd::ProfScope _ps(3, "embedding_fwd", dvd::as_stream(stream));
-  DVD_CHECK_ARG(w && idx && y && n > 0 && dim > 0);
-  embedding_fwd_kernel<<<ew_blocks((int64_t)n * dim, 1), 256, 0, as_stream(stream)>>>(w, idx, n, dim, y);
+  DVD_CHECK_ARG(w && idx && y && n > 0 && dim > 0 && rows > 0);
+  embedding_fwd_kernel<<<ew_blocks((int64_t)n * dim, 1), 256, 0, as_stream(stream)>>>(w, idx, n, dim, rows, y);
   DVD_LAUNCH_CHECK();
   return 0;
 }
-extern "C" int dvd_embedding_bwd(const float* dy, const int64_t* idx, int n, int dim, float* dw, void* stream) {
+extern "C" int dvd_embedding_bwd(const float* dy, const int64_t* idx, int n, int dim, int rows, float* dw,
+                                 void* stream) {
   dvd::ProfScope _ps(3, "embedding_bwd", dvd::as_stream(stream));
-  DVD_CHECK_ARG(dy && idx && dw && n > 0 && dim > 0);
-  embedding_bwd_kernel<<<ew_blocks((int64_t)n * dim, 1), 256, 0, as_stream(stream)>>>(dy, idx, n, dim, dw);
+  DVD_CHECK_ARG(dy && idx && dw && n > 0 && dim > 0 && rows > 0);
+  embedding_bwd_kernel<<<ew_blocks((int64_t)n * dim, 1), 256, 0, as_stream(stream)>>>(dy, idx, n, dim, rows, dw);
   DVD_LAUNCH_CHECK();
   return 0;
 }
-extern "C" int dvd_dhead_fwd(const float* x, int N, int C, int HW, int T, const float* w_lin, const float* sigma_l,
-                             const float* b_lin, const float* emb, const float* sigma_e, const int64_t* class_id,
-                             float* feat, float* out, void* stream) {
+extern "C" int dvd_dhead_fwd(const float* x, int N, int C, int HW, int T, int n_class, const float* w_lin,
+                             const float* sigma_l, const float* b_lin, const float* emb, const float* sigma_e,
+                             const int64_t* class_id, float* feat, float* out, void* stream) {
   dvd::ProfScope _ps(3, "dhead_fwd", dvd::as_stream(stream));
   DVD_CHECK_ARG(x && w_lin && sigma_l && b_lin && emb && sigma_e && class_id && feat && out);
-  DVD_CHECK_ARG(N > 0 && C > 0 && HW > 0 && T > 0);
-  dhead_fwd_kernel<<<N, 256, 0, as_stream(stream)>>>(x, C, HW, T, w_lin, sigma_l, b_lin, emb, sigma_e, class_id, feat,
-                                                     out);
+  DVD_CHECK_ARG(N > 0 && C > 0 && HW > 0 && T > 0 && n_class > 0);
+  dhead_fwd_kernel<<<N, 256, 0, as_stream(stream)>>>(x, C, HW, T, w_lin, sigma_l, b_lin, emb, sigma_e, class_id,
+                                                     n_class, feat, out);
   DVD_LAUNCH_CHECK();
   return 0;
 }
@@ -701,9 +722,22 @@ extern "C" int dvd_dhead_bwd(const float* x, const float* feat, const float* dou
   DVD_CUDA(cudaMemsetAsync(dwl, 0, sizeof(float) * C, st));
   DVD_CUDA(cudaMemsetAsync(db, 0, sizeof(float), st));
   DVD_CUDA(cudaMemsetAsync(demb, 0, sizeof(float) * (size_t)n_class * C, st));
-  dhead_bwd_kernel<<<N, 256, 0, st>>>(x, feat, dout, C, HW, T, w_lin, sigma_l, emb, sigma_e, class_id, dx, dwl, db,
-                                      demb);
+  dhead_bwd_kernel<<<N, 256, 0, st>>>(x, feat, dout, C, HW, T, w_lin, sigma_l, emb, sigma_e, class_id, n_class, dx,
+                                      dwl, db, demb);
   DVD_LAUNCH_CHECK();
+  return 0;
+}
+// Reads (and optionally clears) the count of out-of-range class ids seen by the embedding / head kernels of the
+// current device since the last clear.  The ONE entry point that synchronises: it waits for `stream`.
+extern "C" int dvd_index_errors(unsigned int* count, int reset, void* stream) {
+  DVD_CHECK_ARG(count != nullptr);
+  cudaStream_t st = as_stream(stream);
+  DVD_CUDA(cudaMemcpyFromSymbolAsync(count, g_index_errors, sizeof(unsigned int), 0, cudaMemcpyDeviceToHost, st));
+  if (reset) {
+    const unsigned int zero = 0;
+    DVD_CUDA(cudaMemcpyToSymbolAsync(g_index_errors, &zero, sizeof(unsigned int), 0, cudaMemcpyHostToDevice, st));
+  }
+  DVD_CUDA(cudaStreamSynchronize(st));
   return 0;
 }
 extern "C" int dvd_gan_loss_fwd(const float* x, int n, float sign, int hinge, int accumulate, float* loss,

@@ -318,9 +318,43 @@ class CBNFn(torch.autograd.Function):
         return dx, dgb, None, None, None, None, None, None, None, None
 
 
+# ConvGRU BPTT state policy.  False: keep the activated gates (3Ch) and r*h (Ch) of every frame next to h (Ch) -- 20
+# bytes per hidden element, nothing recomputed.  True ("lean"): keep h only (4 bytes per hidden element) and re-run the
+# layer's forward sweep into transient buffers at the start of its backward (same kernels, same operands -> the same
+# gate values); costs one extra ConvGRU forward per step and is what lets 128x128 clips at 32 per GPU fit 180 GB.
+GRU_LEAN = False
+
+
+def set_gru_lean(flag):
+    global GRU_LEAN
+    GRU_LEAN = bool(flag)
+
+
+def gru_state_bytes(B, T, ch, latent_dim, lean):
+    """fp32 bytes of ConvGRU state the Generator keeps for the backward pass (Generator.py:38-52 stage layout)."""
+    per = 4 if lean else 20
+    total = 0
+    for stage, side in enumerate((latent_dim, 2 * latent_dim, 4 * latent_dim, 8 * latent_dim)):
+        hidden = (4 * ch + 8 * ch + 4 * ch) if stage == 3 else (8 * ch + 16 * ch + 8 * ch)
+        total += B * T * hidden * side * side * per
+    return total
+
+
 class GRULayerFn(torch.autograd.Function):
     """One ConvGRU layer over a clip (ConvGRU.py:29-54 x Generator.py:87-97), BPTT in the backward.
     x: (B,T,Cx,H,W), or (B,Cx,H,W) fed to every frame (Generator.py:88-92, Q13) when T_bcast > 0."""
+
+    @staticmethod
+    def _run_fwd(x, h0, wu, wr, wo, bu, br, bo, cfg):
+        B, T, Cx, Ch, H, W, k, x_bs, x_ts, _ = cfg
+        gates = _new((B, T, 3 * Ch, H, W), x)
+        h = _new((B, T, Ch, H, W), x)
+        rh = _new((B, T, Ch, H, W), x)
+        nbytes = _C.lib().dvd_convgru_layer_workspace_bytes(B, T, Cx, Ch, H, W, k)
+        ws = torch.empty(nbytes, device=x.device, dtype=torch.uint8)
+        call("dvd_convgru_layer_fwd", ptr(x), x_bs, x_ts, ptr(h0), ptr(wu), ptr(wr), ptr(wo), ptr(bu), ptr(br),
+             ptr(bo), ptr(gates), ptr(h), ptr(rh), B, T, Cx, Ch, H, W, k, ptr(ws), nbytes)
+        return gates, h, rh
 
     @staticmethod
     def forward(ctx, x, h0, wu, wr, wo, bu, br, bo, T_bcast):
@@ -336,21 +370,29 @@ class GRULayerFn(torch.autograd.Function):
         Ch, k = wu.shape[0], wu.shape[-1]
         if h0 is not None:
             h0 = _c(h0)
-        gates = _new((B, T, 3 * Ch, H, W), x)
-        h = _new((B, T, Ch, H, W), x)
-        rh = _new((B, T, Ch, H, W), x)
-        nbytes = _C.lib().dvd_convgru_layer_workspace_bytes(B, T, Cx, Ch, H, W, k)
-        ws = torch.empty(nbytes, device=x.device, dtype=torch.uint8)
-        call("dvd_convgru_layer_fwd", ptr(x), x_bs, x_ts, ptr(h0), ptr(wu), ptr(wr), ptr(wo), ptr(bu), ptr(br),
-             ptr(bo), ptr(gates), ptr(h), ptr(rh), B, T, Cx, Ch, H, W, k, ptr(ws), nbytes)
-        ctx.save_for_backward(x, h0, wu, wr, wo, gates, h, rh)
-        ctx.cfg = (B, T, Cx, Ch, H, W, k, x_bs, x_ts, T_bcast)
+        cfg = (B, T, Cx, Ch, H, W, k, x_bs, x_ts, T_bcast)
+        gates, h, rh = GRULayerFn._run_fwd(x, h0, wu, wr, wo, bu, br, bo, cfg)
+        ctx.lean = bool(GRU_LEAN) and torch.is_grad_enabled()
+        if ctx.lean:
+            ctx.save_for_backward(x, h0, wu, wr, wo, bu, br, bo, h)        # gates / rh are dropped here
+        else:
+            ctx.save_for_backward(x, h0, wu, wr, wo, gates, h, rh)
+        ctx.cfg = cfg
+        ctx.consumed = False
         return h
 
     @staticmethod
     def backward(ctx, dh):
-        x, h0, wu, wr, wo, gates, h, rh = ctx.saved_tensors
+        if ctx.consumed:
+            raise RuntimeError("GRULayerFn: second backward through the same graph -- the saved gate buffer was "
+                               "overwritten in place by the first one (the reference trainer backpropagates once)")
+        ctx.consumed = True
         B, T, Cx, Ch, H, W, k, x_bs, x_ts, T_bcast = ctx.cfg
+        if ctx.lean:
+            x, h0, wu, wr, wo, bu, br, bo, h = ctx.saved_tensors
+            gates, _, rh = GRULayerFn._run_fwd(x, h0, wu, wr, wo, bu, br, bo, ctx.cfg)
+        else:
+            x, h0, wu, wr, wo, gates, h, rh = ctx.saved_tensors
         dh = _c(dh)
         dx = _new((B, T, Cx, H, W), x)
         dh0 = _new(h0.shape, x) if h0 is not None else None
@@ -358,10 +400,11 @@ class GRULayerFn(torch.autograd.Function):
         dbu, dbr, dbo = _new((Ch,), x), _new((Ch,), x), _new((Ch,), x)
         nbytes = _C.lib().dvd_convgru_layer_workspace_bytes(B, T, Cx, Ch, H, W, k)
         ws = torch.empty(nbytes, device=x.device, dtype=torch.uint8)
-        # NB: overwrites `gates` in place (single backward pass, as trainer.py does)
+        # NB: overwrites `gates` in place with the pre-activation gradients
         call("dvd_convgru_layer_bwd", ptr(x), x_bs, x_ts, ptr(h0), ptr(wu), ptr(wr), ptr(wo), ptr(gates), ptr(h),
              ptr(rh), ptr(dh), ptr(dx), ptr(dh0), ptr(dwu), ptr(dwr), ptr(dwo), ptr(dbu), ptr(dbr), ptr(dbo), B, T,
              Cx, Ch, H, W, k, ptr(ws), nbytes)
+        del gates, rh
         if T_bcast:
             # sum over frames: dx_sum[b] = ones(1,T) @ dx[b] (T, Cx*H*W)
             ones = torch.ones(T, device=x.device, dtype=F32)
@@ -504,10 +547,11 @@ class EmbeddingFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, idx, w):
-        _C.require_cuda(idx, w)
+        _C.require_cuda(w)
+        _C.require_index(idx)
         n, dim = idx.numel(), w.shape[1]
         y = _new((n, dim), w)
-        call("dvd_embedding_fwd", ptr(w), ptr(idx), n, dim, ptr(y))
+        call("dvd_embedding_fwd", ptr(w), ptr(idx), n, dim, w.shape[0], ptr(y))
         ctx.save_for_backward(idx)
         ctx.shape = w.shape
         return y
@@ -517,7 +561,7 @@ class EmbeddingFn(torch.autograd.Function):
         (idx,) = ctx.saved_tensors
         dy = _c(dy)
         dw = torch.zeros(ctx.shape, device=dy.device, dtype=F32)
-        call("dvd_embedding_bwd", ptr(dy), ptr(idx), idx.numel(), ctx.shape[1], ptr(dw))
+        call("dvd_embedding_bwd", ptr(dy), ptr(idx), idx.numel(), ctx.shape[1], ctx.shape[0], ptr(dw))
         return None, dw
 
 
@@ -527,7 +571,8 @@ class DHeadFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, wl, bl, ul, vl, we, ue, ve, class_id, T):
-        _C.require_cuda(x, wl, we, class_id)
+        _C.require_cuda(x, wl, we)
+        _C.require_index(class_id)
         x = _c(x)
         N, C = x.shape[0], x.shape[1]
         HW = x.numel() // (N * C)
@@ -535,8 +580,8 @@ class DHeadFn(torch.autograd.Function):
         se = sn_sigma(we, ue, ve)
         feat = _new((N, C), x)
         out = _new((N,), x)
-        call("dvd_dhead_fwd", ptr(x), N, C, HW, T, ptr(wl), ptr(sl), ptr(bl), ptr(we), ptr(se), ptr(class_id),
-             ptr(feat), ptr(out))
+        call("dvd_dhead_fwd", ptr(x), N, C, HW, T, we.shape[0], ptr(wl), ptr(sl), ptr(bl), ptr(we), ptr(se),
+             ptr(class_id), ptr(feat), ptr(out))
         ctx.save_for_backward(x, feat, wl, sl, ul, vl, we, se, ue, ve, class_id)
         ctx.cfg = (N, C, HW, T)
         return out
@@ -582,7 +627,8 @@ class GatherFramesFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, idx):
-        _C.require_cuda(x, idx)
+        _C.require_cuda(x)
+        _C.require_index(idx)
         x = _c(x)
         B, T = x.shape[0], x.shape[1]
         k = idx.numel()

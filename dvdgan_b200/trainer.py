@@ -2,10 +2,14 @@
 trainer.py:14-391), on the dvdgan_b200 CUDA kernels.
 
 Differences from the reference that do not change the numbers:
-  * one process per GPU; when torch.distributed is initialised the batch is sharded across ranks and the flat
-    fp32 gradient arena of the network being updated is all-reduced (NCCL, sum) before its Adam step -- the
-    reference's nn.DataParallel (trainer.py:353-359) sums replica gradients the same way; BatchNorm statistics
-    stay per replica in both;
+  * one process per GPU.  ``config.batch_size`` is the GLOBAL batch, as under the reference's nn.DataParallel
+    (trainer.py:353-359): when torch.distributed is initialised every rank draws z / labels / frame subsets for the
+    global batch from the SAME CPU generator stream (rank 0's state is broadcast at construction) and keeps its
+    contiguous shard (``shard_batch``); the flat fp32 gradient arena of the network being updated is summed across
+    ranks (NCCL) before its Adam step, the 1/N folded into the Adam kernel.  BatchNorm statistics stay per
+    replica in both;
+  * ``config.shard_optimizer`` (default off): reduce-scatter of the gradient arena -> Adam on this rank's 1/N slice
+    of (params, m, v) -> all-gather of the parameter arena, instead of all-reduce + N identical full Adam steps;
   * parameters / Adam moments / gradients of each network live in flat arenas: one fused Adam launch and one
     collective per network instead of one per tensor;
   * during the G update the discriminators' parameters do not require grad (the reference computes those
@@ -22,21 +26,33 @@ import torch.distributed as dist
 from . import ops
 from .Module.Discriminators import SpatialDiscriminator, TemporalDiscriminator
 from .Module.Generator import Generator
-from .utils import sample_k_frames, vid_downsample
+from .utils import denorm, sample_k_frames, vid_downsample
 
 
 class FlatAdam:
     """torch.optim.Adam(lr, betas, eps=1e-8) over every requires_grad parameter of ``net`` (trainer.py:136-141),
-    with params, grads and moments in flat fp32 arenas."""
+    with params, grads and moments in flat fp32 arenas.
 
-    def __init__(self, net, lr, betas, eps=1e-8):
+    ``shard=(world, rank)``: ZeRO-1 style -- the arena is padded to a multiple of ``world``; ``step`` reduce-scatters
+    the gradient arena, runs Adam on this rank's slice only (m / v exist only for the slice) and all-gathers the
+    parameter arena in place."""
+
+    def __init__(self, net, lr, betas, eps=1e-8, shard=None):
         self.params = [p for p in net.parameters() if p.requires_grad]
         n = sum(p.numel() for p in self.params)
         dev = self.params[0].device
-        self.flat_p = torch.empty(n, device=dev, dtype=torch.float32)
-        self.flat_g = torch.zeros(n, device=dev, dtype=torch.float32)
-        self.m = torch.zeros(n, device=dev, dtype=torch.float32)
-        self.v = torch.zeros(n, device=dev, dtype=torch.float32)
+        self.shard = shard if (shard and shard[0] > 1) else None
+        world = self.shard[0] if self.shard else 1
+        n_pad = (n + world - 1) // world * world
+        self.flat_p = torch.zeros(n_pad, device=dev, dtype=torch.float32)
+        self.flat_g = torch.zeros(n_pad, device=dev, dtype=torch.float32)
+        n_state = n_pad // world
+        self.m = torch.zeros(n_state, device=dev, dtype=torch.float32)
+        self.v = torch.zeros(n_state, device=dev, dtype=torch.float32)
+        if self.shard:
+            lo = self.shard[1] * n_state
+            self.p_shard = self.flat_p[lo:lo + n_state]
+            self.g_shard = torch.zeros(n_state, device=dev, dtype=torch.float32)
         off = 0
         self.slices = []
         for p in self.params:
@@ -82,21 +98,32 @@ class FlatAdam:
         ops.call("dvd_gather_flat", srcs, offs, cnts, n, ops.ptr(flat))
 
     @staticmethod
-    def _copy(src, flat, off, k):
-        ops.call("dvd_axpby", ops.ptr(src), 1.0, 0.0, k, flat.data_ptr() + 4 * off)
-
-    @staticmethod
     def _adam(p, g, m, v, lr, b1, b2, eps, t, scale):
         ops.adam_step(p, g, m, v, lr, b1, b2, eps, t, scale)
 
+    @staticmethod
+    def _reduce_scatter(out, full):
+        """sum-reduce-scatter of a flat arena; gloo (CPU tests of this host logic) has no reduce_scatter."""
+        if dist.get_backend() == "gloo":
+            dist.all_reduce(full, op=dist.ReduceOp.SUM)
+            n = out.numel()
+            out.copy_(full[dist.get_rank() * n:(dist.get_rank() + 1) * n])
+        else:
+            dist.reduce_scatter_tensor(out, full, op=dist.ReduceOp.SUM)
+
     def step(self, world_size=1):
-        """gather -> (sum all-reduce across ranks) -> fused Adam with the 1/world_size average folded in."""
+        """gather -> (sum across ranks) -> fused Adam with the 1/world_size average folded in."""
         g = self.gather_grads()
+        self.t += 1
+        b1, b2 = self.betas
+        if self.shard and world_size > 1:
+            self._reduce_scatter(self.g_shard, g)
+            self._adam(self.p_shard, self.g_shard, self.m, self.v, self.lr, b1, b2, self.eps, self.t, 1.0 / world_size)
+            dist.all_gather_into_tensor(self.flat_p, self.p_shard)        # in place: the slice sits at its own offset
+            return
         if world_size > 1:
             dist.all_reduce(g, op=dist.ReduceOp.SUM)
-        self.t += 1
-        self._adam(self.flat_p, g, self.m, self.v, self.lr, self.betas[0], self.betas[1], self.eps, self.t,
-                   1.0 / world_size)
+        self._adam(self.flat_p, g, self.m, self.v, self.lr, b1, b2, self.eps, self.t, 1.0 / world_size)
 
 
 def shard_batch(global_batch, world_size, rank):
@@ -135,8 +162,9 @@ def _frozen(*nets):
 
 class Trainer(object):
     """Same constructor contract as the reference: ``Trainer(data_loader, config)``; ``config`` carries the
-    reference's argparse fields (parameter.py:6-79).  ``latent_dim`` (not a reference flag) may be added for
-    128x128 / 256x256 clips."""
+    reference's argparse fields (parameter.py:6-79).  Not reference flags, all optional: ``latent_dim`` (128x128 /
+    256x256 clips), ``gru_lean`` ('auto' | True | False: ConvGRU BPTT keeps h only and recomputes the gates),
+    ``shard_optimizer`` (reduce-scatter / sharded Adam / all-gather), ``sample_path``."""
 
     def __init__(self, data_loader, config):
         self.data_loader = data_loader
@@ -154,8 +182,12 @@ class Trainer(object):
         self.model_save_epoch = getattr(c, "model_save_epoch", 10 ** 9)
         self.test_batch_size = getattr(c, "test_batch_size", 1)
         self.pretrained_model = getattr(c, "pretrained_model", None)
+        self.use_tensorboard = getattr(c, "use_tensorboard", False)
         version = getattr(c, "version", "")
         self.model_save_path = os.path.join(getattr(c, "model_save_path", "./models"), version)
+        self.sample_path = os.path.join(getattr(c, "sample_path", "./samples"), version)
+        self.log_path = os.path.join(getattr(c, "log_path", "./logs"), version)
+        self.shard_optimizer = bool(getattr(c, "shard_optimizer", False))
         if self.adv_loss not in ("hinge", "wgan-gp"):
             raise ValueError("adv_loss must be 'hinge' or 'wgan-gp'")
         if not torch.cuda.is_available():
@@ -164,6 +196,17 @@ class Trainer(object):
         self.world_size = dist.get_world_size() if self.distributed else 1
         self.rank = dist.get_rank() if self.distributed else 0
         self.device = torch.device("cuda", torch.cuda.current_device())
+        self.shard = shard_batch(self.batch_size, self.world_size, self.rank)      # raises if not divisible
+        self.local_batch = self.batch_size // self.world_size
+        lean = getattr(c, "gru_lean", "auto")
+        if lean == "auto":      # full BPTT state (20 B per hidden element) only while it stays under ~1/3 of the device
+            full = ops.gru_state_bytes(self.local_batch, self.n_frames, self.g_chn, self.latent_dim, lean=False)
+            lean = full > 0.35 * torch.cuda.get_device_properties(self.device).total_memory
+        self.gru_lean = bool(lean)
+        ops.set_gru_lean(self.gru_lean)
+        self.writer = None
+        if self.use_tensorboard:
+            self.build_tensorboard()
         self.build_model()
         if self.pretrained_model:
             self.load_pretrained_model()
@@ -178,13 +221,18 @@ class Trainer(object):
             for net in (self.G, self.D_s, self.D_t):
                 for t in list(net.parameters()) + list(net.buffers()):
                     dist.broadcast(t.data, src=0)
+            # ... and draw the same z / labels / frame subsets: one CPU generator stream, rank 0's
+            state = torch.get_rng_state().to(self.device)
+            dist.broadcast(state, src=0)
+            torch.set_rng_state(state.cpu())
         self.select_opt_schr()
 
     def select_opt_schr(self):
         betas = (self.beta1, self.beta2)
-        self.g_optimizer = FlatAdam(self.G, self.g_lr, betas)
-        self.ds_optimizer = FlatAdam(self.D_s, self.d_lr, betas)
-        self.dt_optimizer = FlatAdam(self.D_t, self.d_lr, betas)
+        shard = (self.world_size, self.rank) if (self.shard_optimizer and self.distributed) else None
+        self.g_optimizer = FlatAdam(self.G, self.g_lr, betas, shard=shard)
+        self.ds_optimizer = FlatAdam(self.D_s, self.d_lr, betas, shard=shard)
+        self.dt_optimizer = FlatAdam(self.D_t, self.d_lr, betas, shard=shard)
         _lr_at(self.lr_schr, 1.0, 0, self.lr_decay)     # validates lr_schr
 
     def _sched_step(self, opt):
@@ -196,8 +244,9 @@ class Trainer(object):
         self.g_optimizer.zero_grad()
 
     def label_sample(self):
+        """trainer.py:84-88 for the GLOBAL batch; this rank's shard goes to the device."""
         label = torch.randint(low=0, high=self.n_class, size=(self.batch_size,))
-        return label.to(self.device)
+        return label[self.shard].to(self.device)
 
     def calc_loss(self, x, real_flag, y=None, y_real_flag=None):
         """trainer.py:114-121; with ``y`` the two-term sum loss(x) + loss(y) in one op."""
@@ -206,13 +255,30 @@ class Trainer(object):
         sy = -1.0 if y_real_flag is True else 1.0
         return ops.GanLossFn.apply(hinge, sx, x, sy, y)
 
+    def _local(self, real_videos, real_labels):
+        """Accept the loader's global batch (sliced to this rank's shard) or an already-local shard; enforce the
+        dtypes the kernels assume (the reference's modules would raise or cast on anything else)."""
+        if real_videos.shape[0] == self.batch_size and self.world_size > 1:
+            real_videos, real_labels = real_videos[self.shard], real_labels[self.shard]
+        if real_videos.shape[0] != self.local_batch:
+            raise ValueError(f"expected {self.local_batch} clips per rank (global batch {self.batch_size} over "
+                             f"{self.world_size} ranks), got {real_videos.shape[0]}")
+        if not real_labels.is_cuda:         # host labels: range-check for free (device labels are the caller's contract)
+            if real_labels.numel() and (int(real_labels.min()) < 0 or int(real_labels.max()) >= self.n_class):
+                raise IndexError(f"class id out of range [0, {self.n_class})")
+        real_videos = real_videos.to(self.device, dtype=torch.float32, non_blocking=True)
+        real_labels = real_labels.to(self.device, dtype=torch.int64, non_blocking=True)
+        return real_videos, real_labels
+
     # ------------------------------------------------------------------ one step (trainer.py:229-307)
     def train_step(self, real_videos, real_labels):
-        """real_videos (B,C,T,H,W) on the device (as the loader yields them), real_labels (B,) int64."""
+        """real_videos (B,C,T,H,W) as the loader yields them (global batch or this rank's shard; host or device),
+        real_labels (B,) integer class ids."""
+        real_videos, real_labels = self._local(real_videos, real_labels)
         real_videos = ops.Permute5Fn.apply(real_videos, (0, 2, 1, 3, 4))       # -> B,T,C,H,W
         for _ in range(self.d_iters):
             real_s = sample_k_frames(real_videos, self.n_frames, self.k_sample)
-            z = torch.randn(self.batch_size, self.z_dim).to(self.device)
+            z = torch.randn(self.batch_size, self.z_dim)[self.shard].to(self.device)
             z_class = self.label_sample()
             fake_videos = self.G(z, z_class)
             fv_s, fv_t = ops.fork(fake_videos, 2)
@@ -239,12 +305,15 @@ class Trainer(object):
         with _frozen(self.D_s, self.D_t):
             g_s = self.D_s(fake_s, z_class)
             g_t = self.D_t(fake_d, z_class)
-            g_loss = self.calc_loss(g_s, True, g_t, True)
+            g_s_loss = self.calc_loss(g_s, True)
+            g_t_loss = self.calc_loss(g_t, True)
+            g_loss = ops.AddFn.apply(g_s_loss.view(1), g_t_loss.view(1)).view(())
             self.reset_grad()
             g_loss.backward()
         self.g_optimizer.step(self.world_size)
         self._sched_step(self.g_optimizer)
-        return {"ds_loss": ds_loss.detach(), "dt_loss": dt_loss.detach(), "g_loss": g_loss.detach()}
+        return {"ds_loss": ds_loss.detach(), "dt_loss": dt_loss.detach(), "g_loss": g_loss.detach(),
+                "g_s_loss": g_s_loss.detach(), "g_t_loss": g_t_loss.detach()}
 
     # ------------------------------------------------------------------ loop (trainer.py:189-343)
     def epoch2step(self):
@@ -252,13 +321,16 @@ class Trainer(object):
         step_per_epoch = len(self.data_loader)
         self.total_step = self.total_epoch * step_per_epoch
         self.log_step = self.log_epoch * step_per_epoch
+        self.sample_step = self.sample_epoch * step_per_epoch
         self.model_save_step = self.model_save_epoch * step_per_epoch
 
     def train(self):
         data_iter = iter(self.data_loader)
         self.epoch2step()
-        # consumed to keep the CPU RNG stream aligned with the reference (trainer.py:195)
+        # trainer.py:195-197 (the reference leaves fixed_label on the host, which fails on a GPU run; here it moves)
         self.fixed_z = torch.randn(self.test_batch_size * self.n_class, self.z_dim).to(self.device)
+        self.fixed_label = torch.tensor([i for i in range(self.n_class) for _ in range(self.test_batch_size)],
+                                        dtype=torch.int64).to(self.device)
         start = self.pretrained_model + 1 if self.pretrained_model else 1
         start_time = time.time()
         self.D_s.train(); self.D_t.train(); self.G.train()
@@ -270,19 +342,75 @@ class Trainer(object):
                 data_iter = iter(self.data_loader)
                 real_videos, real_labels = next(data_iter)
                 self.epoch += 1
-            real_videos = real_videos.to(self.device, non_blocking=True)
-            real_labels = real_labels.to(self.device, non_blocking=True)
             out = self.train_step(real_videos, real_labels)
             history.append(out)
             if step % self.log_step == 0 and self.rank == 0:
                 elapsed = time.time() - start_time
                 start_time = time.time()
-                print("Epoch: [%d/%d], Step: [%d/%d], time: %.1fs, ds_loss: %.4f, dt_loss: %.4f, g_loss: %.4f, lr: %.2e"
-                      % (self.epoch, self.total_epoch, step, self.total_step, elapsed, float(out["ds_loss"]),
-                         float(out["dt_loss"]), float(out["g_loss"]), self.g_optimizer.lr))
+                log_str = ("Epoch: [%d/%d], Step: [%d/%d], time: %.1fs, ds_loss: %.4f, dt_loss: %.4f, g_s_loss: %.4f, "
+                           "g_t_loss: %.4f, g_loss: %.4f, lr: %.2e"
+                           % (self.epoch, self.total_epoch, step, self.total_step, elapsed, float(out["ds_loss"]),
+                              float(out["dt_loss"]), float(out["g_s_loss"]), float(out["g_t_loss"]),
+                              float(out["g_loss"]), self.g_optimizer.lr))
+                if self.writer is not None:
+                    for k in ("ds_loss", "dt_loss", "g_loss"):
+                        self.writer.add_scalar("data/" + k, float(out[k]), step)
+                    self.writer.add_text("logs", log_str, step)
+                print(log_str)
+            if step % self.sample_step == 0 and self.rank == 0:
+                self.sample(step)
             if step % self.model_save_step == 0 and self.rank == 0:
                 self.save_models(step)
         return history
+
+    # ------------------------------------------------------------------ sampling (trainer.py:322-334)
+    @torch.no_grad()
+    def sample(self, step, save=True):
+        """G in eval mode (running BatchNorm statistics; the spectral norms still advance u, v -- Q3) on the fixed
+        noise / one label per class; returns the de-normalised clips (n_class * test_batch_size, T, 3, H, W) in [0, 1]
+        and writes one image grid per clip (frames side by side) like the reference's save_image call."""
+        if not hasattr(self, "fixed_z"):
+            self.fixed_z = torch.randn(self.test_batch_size * self.n_class, self.z_dim).to(self.device)
+            self.fixed_label = torch.tensor([i for i in range(self.n_class) for _ in range(self.test_batch_size)],
+                                            dtype=torch.int64).to(self.device)
+        was_training = self.G.training
+        self.G.eval()
+        outs = []
+        chunk = max(1, self.local_batch)
+        for i in range(0, self.fixed_z.shape[0], chunk):            # bounded memory for n_class = 101 / 600
+            fake = self.G(self.fixed_z[i:i + chunk], self.fixed_label[i:i + chunk])
+            outs.append(denorm(fake.detach().clone()))
+        self.G.train(was_training)
+        videos = torch.cat(outs, 0)
+        if save:
+            os.makedirs(self.sample_path, exist_ok=True)
+            try:
+                from torchvision.utils import make_grid, save_image
+            except Exception:           # no torchvision: keep the tensors
+                save_image = make_grid = None
+            for i in range(self.n_class):
+                for j in range(self.test_batch_size):
+                    clip = videos[i * self.test_batch_size + j]
+                    name = "Class_%d_No.%d_Step_%d" % (i, j, step)
+                    if self.writer is not None and make_grid is not None:
+                        self.writer.add_image(name.replace("_Step", "/Step"), make_grid(clip.cpu()), step)
+                    elif save_image is not None:
+                        save_image(clip.cpu(), os.path.join(self.sample_path, name + ".png"))
+                    else:
+                        torch.save(clip.cpu(), os.path.join(self.sample_path, name + ".pt"))
+        return videos
+
+    def build_tensorboard(self):
+        """trainer.py:368-373; tensorboardX is optional (absent in this image): without it scalars go to stdout only."""
+        try:
+            from tensorboardX import SummaryWriter
+        except Exception:
+            try:
+                from torch.utils.tensorboard import SummaryWriter
+            except Exception:
+                self.writer = None
+                return
+        self.writer = SummaryWriter(log_dir=self.log_path)
 
     # ------------------------------------------------------------------ checkpoints (trainer.py:336-343,375-382)
     def save_models(self, step):
@@ -298,6 +426,9 @@ class Trainer(object):
     def _load_sd(net, sd, path="<state_dict>"):
         sd = {(k[len("module."):] if k.startswith("module.") else k): v for k, v in sd.items()}  # DataParallel files
         own = net.state_dict()
+        unexpected = set(sd) - set(own)
+        if unexpected:
+            raise KeyError(f"unexpected keys in {path}: {sorted(unexpected)[:5]}")
         for k, v in sd.items():
             own[k].copy_(v)          # in place: parameters stay views of the flat arena
         missing = set(own) - set(sd)

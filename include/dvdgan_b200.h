@@ -8,8 +8,12 @@
  *
  * Conventions
  *  - all tensors are fp32, device memory, caller-owned; class ids / frame indices are int64.
- *  - every call only enqueues work on `stream` (a cudaStream_t passed as void*); no host sync,
- *    no allocation, no global mutable state => re-entrant per (device, stream).
+ *  - every call only enqueues work on `stream` (a cudaStream_t passed as void*) of the CURRENT device; no host sync
+ *    (except dvd_index_errors and the dvd_prof_* measurement aids).  Persistent buffers are the caller's; the
+ *    tensor-core engine additionally takes stream-ordered scratch for its operand planes from the device's default
+ *    cudaMallocAsync pool (dvd_scratch_bytes).  Re-entrant per (device, stream): one-time kernel attributes and pool
+ *    settings are tracked per device; the only process-wide state is the option table (dvd_set_option), the launch
+ *    counter and the profiler.
  *  - return value: 0 = ok, non-zero = error; dvd_last_error() gives a thread-local message.
  *  - "packed" conv weights: [tap][Cin][Cout] (Cout contiguous), produced by dvd_weight_pack.
  */
@@ -36,6 +40,20 @@ int dvd_prof_read(int category, double* ms, double* flops, long long* launches);
  * category 2 = operand-plane preparation of the tcgen05 engine (value column = bytes moved) */
 int dvd_prof_dump(const char* path);
 
+/* Process-wide tuning switches (atomic; read at every call, so they can be flipped between calls).  Defaults are the
+ * validated configuration; nothing is read from the environment inside the library.
+ *   "simt_only" 0   fp32 FFMA conv engine for every convolution (the tests' cross-check of the tensor-core engine)
+ *   "pair" 1, "persist" 1, "occ2" 1, "epi_prefetch" 1     tile / scheduling variants of the tcgen05 engine
+ *   "oneacc" 0      persistent tiles use ONE fp32 accumulator for all three bf16 products and double-buffer it
+ *   "gru_fused" 1, "gru_share_planes" 1, "gru_bwd_planes" 1   ConvGRU fusion levels
+ *   "flash_attn" 1  attention on the tensor cores without the N x N map (0: materialised SIMT path)
+ * Unknown names are an error. */
+int dvd_set_option(const char* name, int value);
+int dvd_get_option(const char* name, int* value);
+/* High-water mark / currently reserved bytes of the current device's default stream-ordered memory pool: the bf16
+ * operand planes of the tensor-core engine are cudaMallocAsync'ed there (freed in stream order after each call). */
+int dvd_scratch_bytes(long long* high_water, long long* reserved);
+
 /* ------------------------------------------------------------------------------------------
  * Dense engines
  * ---------------------------------------------------------------------------------------- */
@@ -58,8 +76,7 @@ typedef struct {
   int out_act;                /* 0 none, 1 relu, 2 tanh (applied after bias / residual) */
   int res_up;                 /* residual is read at (h>>res_up, w>>res_up) */
   int64_t r_s1, r_s2, r_cs;   /* residual strides (if res != NULL) */
-  int x_kind;                 /* tensor-core path hint: 1 = x holds forward activations (O(1e-4..1e4) magnitudes:
-                                 the low-order split plane may be fp16), 0 = x may hold gradients (bf16 plane) */
+  int x_kind;                 /* reserved (ABI 1 used it to pick fp16 operand planes; all planes are bf16 now) */
 } dvd_conv_desc;
 
 int dvd_conv_fwd(const dvd_conv_desc* d, const float* x, const float* w_packed, const float* bias,
@@ -202,14 +219,18 @@ int dvd_axpby(const float* x, float a, float b, int64_t n, float* y, void* strea
  * launches.  srcs / offs / counts are HOST arrays of device pointers / element offsets / element counts. */
 int dvd_gather_flat(const float* const* srcs, const int64_t* offs, const int64_t* counts, int n, float* flat, void* stream);
 /* Embedding rows (Generator.py:70): y[i] = w[idx[i]]; bwd: dw[idx[i]] += dy[i] (dw pre-zeroed by caller). */
-int dvd_embedding_fwd(const float* w, const int64_t* idx, int n, int dim, float* y, void* stream);
-int dvd_embedding_bwd(const float* dy, const int64_t* idx, int n, int dim, float* dw, void* stream);
+int dvd_embedding_fwd(const float* w, const int64_t* idx, int n, int dim, int rows, float* y, void* stream);
+int dvd_embedding_bwd(const float* dy, const int64_t* idx, int n, int dim, int rows, float* dw, void* stream);
+/* nn.Embedding raises on an index outside [0, rows); the kernels above and the head below count such ids (and clamp
+ * them so no access leaves the table).  Reads -- and with reset != 0 clears -- the current device's count.  This is the
+ * one entry point that synchronises (it waits for `stream`). */
+int dvd_index_errors(unsigned int* count, int reset, void* stream);
 
 /* Discriminator head (Discriminators.py:264-291, 421-447): feat[n][c] = sum_hw relu(x);
  * out[n] = feat . w_lin/sigma_l + b + feat . emb[class[n / T]]/sigma_e. */
-int dvd_dhead_fwd(const float* x, int N, int C, int HW, int T, const float* w_lin, const float* sigma_l,
-                  const float* b_lin, const float* emb, const float* sigma_e, const int64_t* class_id, float* feat,
-                  float* out, void* stream);
+int dvd_dhead_fwd(const float* x, int N, int C, int HW, int T, int n_class, const float* w_lin,
+                  const float* sigma_l, const float* b_lin, const float* emb, const float* sigma_e,
+                  const int64_t* class_id, float* feat, float* out, void* stream);
 /* Grads wrt x, W_lin_sn (dwl[C]), bias (db[1]) and Emb_sn (demb[n_class][C]); outputs are overwritten. */
 int dvd_dhead_bwd(const float* x, const float* feat, const float* dout, int N, int C, int HW, int T, int n_class,
                   const float* w_lin, const float* sigma_l, const float* emb, const float* sigma_e,

@@ -1,5 +1,5 @@
 """Micro-benchmark of the conv engine on the ConvGRU / GResBlock shapes of config 2 (B=64).
-usage: [DVD_CONV_IMPL=simt|tc] python profiles/conv_microbench.py [--reps R] [--only NAME] [--err]
+usage: [DVD_OPTIONS=oneacc=1,...] python profiles/conv_microbench.py [--reps R] [--only NAME] [--err] [--acc]
 Prints TFLOP/s (algorithmic, 2*MAC) per shape for forward and weight-gradient, and with --err the rel-L2 error
 of the forward against an fp64 CPU reference on a slice."""
 import argparse
@@ -32,9 +32,10 @@ def main():
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--only", default=None)
     ap.add_argument("--err", action="store_true")
+    ap.add_argument("--acc", action="store_true", help="forward in accumulate mode (y += conv(x)), the per-timestep GEMMs' epilogue")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
-    print("impl:", os.environ.get("DVD_CONV_IMPL", "tc (default)"))
+    print("options:", os.environ.get("DVD_OPTIONS", "(defaults)"), "accumulate" if a.acc else "")
     for name, (N, Ci, Co, H, W, k) in SHAPES.items():
         if a.only and a.only != name:
             continue
@@ -45,9 +46,10 @@ def main():
         wp = ops.pack_weight(w)
         flops = 2.0 * N * H * W * Co * Ci * k * k
         res = {}
+        ybuf = torch.zeros(N, Co, H, W, device=dev)
         for what in ("fwd", "wgrad"):
-            fn = (lambda: ops.conv_raw(x, wp, None, Co, (1, k, k))) if what == "fwd" else \
-                (lambda: ops.wgrad_raw(x, dy, (1, k, k)))
+            fn = (lambda: ops.conv_raw(x, wp, None, Co, (1, k, k), out=ybuf, accumulate=int(a.acc))) if what == "fwd" \
+                else (lambda: ops.wgrad_raw(x, dy, (1, k, k)))
             fn()
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -1,22 +1,43 @@
 #!/bin/bash
-# One gpurun call: GPU parity tests, the bench line, the per-shape event profile, the conv micro-benchmark, one
-# `ncu --set full` capture of the dominant kernels and an ncu launch list.  Outputs land in gpurun_out/<tag>/ (scratch);
-# the summaries are copied into profiles/ afterwards.
+# One gpurun call of round 2.  Stages (space-separated in $STAGES, default: all of "tests bench configs oneacc"):
+#   tests    pytest -m gpu
+#   bench    the default bench line (config 2) with the per-shape event profile
+#   configs  bench lines of BASELINE.json configs 3, 4, 5 at their per-GPU batch on ONE GPU
+#   oneacc   A/B of the double-buffered single-accumulator tiles: micro-benchmark, Generator error by stage, bench line
+#   ncu      `ncu --set full` of the dominant kernels + the launch list of a --frames 8 step
+# Outputs land in gpurun_out/<tag>/ (scratch); summaries are copied into profiles/ afterwards.
 #   usage: gpurun --timeout 2400 -- bash profiles/run_gpu_round.sh [tag]
-# The ncu launch list costs ~0.18 s per launch on this box; a full config-2 step is ~13 k launches (40 min), so the list
-# is taken on the same bench command with --frames 8 (same kernels, same shapes per step, 1/6 of the time steps) and the
-# bench's own per-shape CUDA-event table is written for BOTH the reduced and the full command for comparison.
-TAG=${1:-r1}
+TAG=${1:-r2}
+STAGES=${STAGES:-tests bench configs oneacc}
 O=gpurun_out/$TAG
 mkdir -p $O
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.used --format=csv > $O/smi.txt 2>&1
-if [ -z "$SKIP_TESTS" ]; then
-  timeout 900 python -m pytest tests -m gpu -x -q > $O/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a $O/pytest_gpu.log
-  tail -5 $O/pytest_gpu.log
+nproc > $O/nproc.txt
+has() { [[ " $STAGES " == *" $1 "* ]]; }
+if has tests; then
+  timeout ${TEST_TIMEOUT:-1500} python -m pytest tests -m gpu -x -q --durations=15 > $O/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a $O/pytest_gpu.log
+  tail -30 $O/pytest_gpu.log
 fi
-timeout 600 python bench.py --prof-dump $O/prof_full.tsv > $O/bench.json 2> $O/bench.err; echo "bench rc=$?"; cat $O/bench.json
-timeout 300 python profiles/conv_microbench.py --reps 5 --err > $O/microbench.txt 2>&1; cat $O/microbench.txt
-if [ -z "$SKIP_NCU" ]; then
+if has bench; then
+  timeout 600 python bench.py --prof-dump $O/prof_full.tsv > $O/bench.json 2> $O/bench.err; echo "bench rc=$?"; cat $O/bench.json; tail -3 $O/bench.err
+fi
+if has configs; then
+  for c in 3 4 5; do
+    timeout 600 python bench.py --config $c --steps 2 --warmup 3 --no-cpu-baseline --prof-dump $O/prof_c$c.tsv \
+        > $O/bench_c$c.json 2> $O/bench_c$c.err; echo "bench config $c rc=$?"; cat $O/bench_c$c.json; tail -3 $O/bench_c$c.err
+  done
+fi
+if has oneacc; then
+  for o in "oneacc=0" "oneacc=1"; do
+    echo "== $o" | tee -a $O/microbench_oneacc.txt
+    DVD_OPTIONS=$o timeout 200 python profiles/conv_microbench.py --reps 5 --err --acc >> $O/microbench_oneacc.txt 2>&1
+  done
+  cat $O/microbench_oneacc.txt
+  timeout 400 python profiles/g_error_by_stage.py 0 oneacc=0 oneacc=1 > $O/g_error_oneacc.txt 2>&1; cat $O/g_error_oneacc.txt
+  DVD_OPTIONS=oneacc=1 timeout 400 python bench.py --no-cpu-baseline --prof-dump $O/prof_oneacc.tsv > $O/bench_oneacc.json 2> $O/bench_oneacc.err
+  echo "bench oneacc rc=$?"; cat $O/bench_oneacc.json
+fi
+if has ncu; then
   timeout 400 ncu --set full --clock-control none --import-source on -k regex:conv_tma_ -c 4 -f -o $O/conv_tma_s9 \
       python profiles/conv_microbench.py --reps 1 --only s9_cell1_h_ur > $O/ncu_full.log 2>&1; echo "ncu full rc=$?"
   timeout 300 python bench.py --frames 8 --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --prof-dump $O/prof_f8.tsv \

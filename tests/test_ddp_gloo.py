@@ -33,7 +33,7 @@ def _cpu_adam(p, g, m, v, lr, b1, b2, eps, t, scale):
     p.addcdiv_(m, (v.sqrt() / bc2 ** 0.5).add_(eps), value=-lr / bc1)
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, shard=False):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -43,8 +43,10 @@ def _worker(rank, world, port, q):
     FlatAdam._adam = staticmethod(_cpu_adam)
     torch.manual_seed(0)                       # identical replicas
     net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 1))
-    opt = FlatAdam(net, 1e-2, (0.0, 0.9))
+    opt = FlatAdam(net, 1e-2, (0.0, 0.9), shard=(world, rank) if shard else None)
     assert all(p.data_ptr() >= opt.flat_p.data_ptr() for p in net.parameters())   # params are arena views
+    if shard:       # 41 parameters over 2 ranks: arena padded to 42, moments exist for this rank's 21 only
+        assert opt.flat_p.numel() == 42 and opt.m.numel() == 21 and opt.v.numel() == 21
     x = torch.randn(8, 6)
     y = torch.randn(8, 1)
     sl = shard_batch(8, world, rank)
@@ -53,17 +55,18 @@ def _worker(rank, world, port, q):
         loss = ((net(x[sl]) - y[sl]) ** 2).mean()
         loss.backward()
         opt.step(world)
-    q.put((rank, opt.flat_p.clone()))
+    q.put((rank, opt.flat_p[:opt.numel].clone()))
     dist.barrier()
     dist.destroy_process_group()
 
 
-def test_flat_adam_allreduce_matches_global_batch():
+@pytest.mark.parametrize("shard", [False, True], ids=["allreduce", "reduce_scatter_sharded_adam_all_gather"])
+def test_flat_adam_allreduce_matches_global_batch(shard):
     world = 2
-    port = 29500 + os.getpid() % 2000
+    port = 29500 + (os.getpid() + 7 * shard) % 2000
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, shard)) for r in range(world)]
     for p in procs:
         p.start()
     res = dict(q.get(timeout=120) for _ in range(world))

@@ -33,7 +33,7 @@ def test_header_symbols_exported(lib_path):
 def test_binding_covers_header(lib_path):
     from dvdgan_b200 import _C
     assert sorted(_C.EXPORTS) == _declared()
-    assert _C.lib().dvd_abi_version() == 1
+    assert _C.lib().dvd_abi_version() == 2
 
 
 def test_sass_is_sm100(lib_path):
