@@ -316,6 +316,7 @@ def run_b200(a):
     mem_gb = torch.cuda.max_memory_allocated() / 2 ** 30
     scratch_hw, _ = _C.scratch_bytes()          # operand planes live in the cudaMallocAsync pool, outside torch's allocator
     bad_ids = _C.index_errors()
+    saturated = _C.saturation_count()
 
     if rank == 0:
         clips = B * world * a.steps
@@ -364,7 +365,7 @@ def run_b200(a):
             "clocks": clocks,
             "peak_mem_gib": mem_gb + scratch_hw / 2 ** 30,
             "peak_mem_detail_gib": {"torch_allocator": mem_gb, "operand_plane_pool_high_water": scratch_hw / 2 ** 30},
-            "out_of_range_class_ids": bad_ids,
+            "out_of_range_class_ids": bad_ids, "fp16_saturated_operand_groups": saturated,
             "last_losses": losses[-1] if losses else None,
         }
         if world == 1 and not a.no_cpu_baseline:

@@ -34,18 +34,16 @@ class GResBlock(nn.Module):
             raise NotImplementedError("upsample_factor must be 1 or 2")
         up = 1 if self.upsample_factor == 2 else 0
         xa, xb = ops.fork(x, 2)
-        if self.bn:
-            out = self.CBNorm1.fused(xa, condition, relu=True, up=up)
-            out = self.conv0.conv(out)
-            out = self.CBNorm2.fused(out, condition, relu=True)
-            pre_relu = 0
-        else:
-            out = self.conv0.conv(xa, in_relu=1, in_up=up)
-            pre_relu = 1
         # conv_sc is 1x1, so it commutes with the nearest upsample (Q14): run it at low resolution and
         # add its upsampled output in conv1's epilogue.
         skip = self.conv_sc.conv(xb)
-        out = self.conv1.conv(out, res=skip, in_relu=pre_relu, res_up=up)
+        if self.bn:
+            # each (CBN -> ReLU -> [up] -> conv) pair is one autograd node that keeps only its pre-norm input
+            out = self.CBNorm1.fused_conv(xa, condition, self.conv0, up=up)
+            out = self.CBNorm2.fused_conv(out, condition, self.conv1, res=skip, res_up=up)
+        else:
+            out = self.conv0.conv(xa, in_relu=1, in_up=up)
+            out = self.conv1.conv(out, res=skip, in_relu=1, res_up=up)
         if self.downsample_factor != 1:
             d = self.downsample_factor
             out = ops.AvgPoolFn.apply(out, 1, d, d)

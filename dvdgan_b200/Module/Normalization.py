@@ -105,5 +105,18 @@ class ConditionalNorm(nn.Module):
         return ops.CBNFn.apply(x, gb, bn.running_mean, bn.running_var, bn.num_batches_tracked, relu, up,
                                use_batch, momentum, bn.eps)
 
+    def fused_conv(self, x, class_id, sn_conv, up=0, res=None, res_up=0):
+        """ConditionalNorm -> ReLU -> [nearest x2] -> ``sn_conv`` (a SpectralNorm-wrapped conv) [+ residual] without
+        keeping the normalised activation for the backward (ops.CBNConvFn)."""
+        gb = ops.conv(class_id, self.embed.weight, self.embed.bias)
+        bn = self.bn
+        use_batch = self.training or bn.running_mean is None
+        momentum = 0.1 if bn.momentum is None else bn.momentum
+        m = sn_conv.module
+        w, u, v = sn_conv._wuv()
+        sn_conv._extra_iterations()
+        return ops.CBNConvFn.apply(x, gb, bn.running_mean, bn.running_var, bn.num_batches_tracked, up, use_batch,
+                                   momentum, bn.eps, w, m.bias, u.data, v.data, res, res_up)
+
     def forward(self, x, class_id):
         return self.fused(x, class_id)

@@ -34,6 +34,7 @@ _SIGS = {
                           ctypes.POINTER(ctypes.c_longlong)]),
     "dvd_set_option": (I, [ctypes.c_char_p, I]),
     "dvd_get_option": (I, [ctypes.c_char_p, ctypes.POINTER(c_int)]),
+    "dvd_saturation_count": (I, [ctypes.POINTER(ctypes.c_uint), I, P]),
     "dvd_scratch_bytes": (I, [ctypes.POINTER(ctypes.c_longlong), ctypes.POINTER(ctypes.c_longlong)]),
     "dvd_conv_fwd": (I, [ctypes.POINTER(ConvDesc), P, P, P, P, P, P]),
     "dvd_conv_wgrad": (I, [ctypes.POINTER(ConvDesc), P, P, P, P]),
@@ -50,6 +51,10 @@ _SIGS = {
     "dvd_cbn_bwd": (I, [P, P, I, P, P, P, I, I, I, I, I, I, I, P, P, P, P]),
     "dvd_attn_fwd": (I, [P, L, P, L, P, L, P, P, L, I, I, I, I, I, I, P]),
     "dvd_attn_bwd": (I, [P, L, P, L, P, L, P, P, P, L, P, L, P, L, P, L, I, I, I, I, I, I, P]),
+    "dvd_attn_flash_supported": (I, [I, I, I, I, I, I]),
+    "dvd_attn_flash_workspace_bytes": (Z, [I, I, I, I, I, I]),
+    "dvd_attn_flash_fwd": (I, [P, L, P, L, P, L, P, L, P, I, I, I, I, I, P, Z, P]),
+    "dvd_attn_flash_bwd": (I, [P, L, P, L, P, L, P, L, P, L, P, P, L, P, L, P, L, I, I, I, I, I, P, Z, P]),
     "dvd_avgpool_fwd": (I, [P, L, I, I, I, I, I, I, F, I, P, P]),
     "dvd_avgpool_bwd": (I, [P, L, I, I, I, I, I, I, I, P, P]),
     "dvd_maxpool_fwd": (I, [P, L, I, I, I, I, I, I, P, P]),
@@ -120,6 +125,14 @@ def index_errors(reset=True):
     n = ctypes.c_uint()
     rc = lib().dvd_index_errors(ctypes.byref(n), int(reset), stream())
     if rc != 0:
+        raise RuntimeError(lib().dvd_last_error().decode())
+    return n.value
+
+
+def saturation_count(reset=True):
+    """8-element operand groups clamped to fp16's range by the forward planes on the current device (synchronises)."""
+    n = ctypes.c_uint()
+    if lib().dvd_saturation_count(ctypes.byref(n), int(reset), stream()) != 0:
         raise RuntimeError(lib().dvd_last_error().decode())
     return n.value
 

@@ -20,13 +20,15 @@ enum Option {
   OPT_PAIR,              // "pair":        cta_group::2 CTA-pair tiles (1)
   OPT_PERSIST,           // "persist":     persistent CTA pairs when there is more than one wave of tiles (1)
   OPT_ONEACC,            // "oneacc":      persistent tiles accumulate all three MMA products into ONE fp32 TMEM
-                         //                accumulator and double-buffer it (epilogue hidden under the next tile)
+                         //                accumulator and double-buffer it (epilogue hidden under the next tile);
+                         //                implies bf16 planes in the forward (0)
   OPT_OCC2,              // "occ2":        two CTAs per SM for short reductions on narrow tiles (1)
   OPT_EPI_PREFETCH,      // "epi_prefetch": L2 prefetch of the epilogue operands late in the main loop (1)
   OPT_GRU_FUSED,         // "gru_fused":   ConvGRU gate math in the h-half GEMM epilogues (1)
   OPT_GRU_SHARE_PLANES,  // "gru_share_planes": BPTT gate-gradient planes shared by x-dgrad and the weight gradients (1)
   OPT_GRU_BWD_PLANES,    // "gru_bwd_planes":  the BPTT elementwise kernels write those planes themselves (1)
   OPT_FLASH_ATTN,        // "flash_attn":  tcgen05 attention that never materialises the N x N map (1)
+  OPT_FWD_BF16,          // "fwd_bf16":    bf16 operand planes in the forward too (fp32 range, 16-bit operand precision) (0)
   OPT_COUNT
 };
 int get_option(int opt);

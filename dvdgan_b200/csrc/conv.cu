@@ -867,7 +867,7 @@ namespace {
 struct OptDef { const char* name; int def; };
 const OptDef kOptDefs[OPT_COUNT] = {
     {"simt_only", 0}, {"pair", 1}, {"persist", 1}, {"oneacc", 0}, {"occ2", 1}, {"epi_prefetch", 1},
-    {"gru_fused", 1}, {"gru_share_planes", 1}, {"gru_bwd_planes", 1}, {"flash_attn", 1},
+    {"gru_fused", 1}, {"gru_share_planes", 1}, {"gru_bwd_planes", 1}, {"flash_attn", 1}, {"fwd_bf16", 0},
 };
 std::atomic<int> g_opts[OPT_COUNT];
 std::atomic<bool> g_opts_init{false};
@@ -906,6 +906,13 @@ extern "C" int dvd_get_option(const char* name, int* value) {
   if (i < 0) return dvd::fail("unknown option '%s' (%s:%d)", name, __FILE__, __LINE__);
   *value = dvd::g_opts[i].load(std::memory_order_relaxed);
   return 0;
+}
+
+// Forward operands are split into fp16 planes (22 bits); elements beyond +-65504 are clamped there.  Reads -- and with
+// reset != 0 clears -- the number of 8-element groups that were clamped on the current device.  Synchronises `stream`.
+extern "C" int dvd_saturation_count(unsigned int* count, int reset, void* stream) {
+  DVD_CHECK_ARG(count != nullptr);
+  return dvd::tma_saturation_count(count, reset, dvd::as_stream(stream));
 }
 
 // High-water mark (bytes) of the current device's default stream-ordered memory pool: the operand planes of the

@@ -19,7 +19,7 @@ int zero_output_view(const ConvP& p, cudaStream_t st);
 
 // Optional extras of the TMA + tcgen05 forward engine (library-internal, used by the ConvGRU time loop).
 // Pre-split operand planes: activations [N][D*H*W][CinP] and weights [taps][CoutP][CinP], each as a hi and a lo
-// bf16 plane (x = hi + lo, see conv_tma.cu).
+// plane of 16-bit floats (fp16 with lo scaled by 2^11 for forward operands, bf16 otherwise; see conv_tma.cu).
 struct TmaOperands {
   const void* a_hi = nullptr;     // nullptr: split p.x inside the call
   const void* a_lo = nullptr;
@@ -37,7 +37,7 @@ struct TmaOperands {
 //                                                co >= Ch: y = r = sigmoid(v); out2 = r * hprev  (+ planes of it)
 //  mode 2 (h-half of out, Cout = Ch):            y = o = tanh(v); out2 = hprev * (1 - u) + o * u  (+ planes of it)
 // hprev / ugate / out2 are (B, Ch, H, W) views with batch strides hp_s1 / u_s1 / o2_s1 and channel stride H*W;
-// the planes are dense [B*H*W][pl_Cp] bf16 (hi, lo), the A operand of the next h-half GEMM.
+// the planes are dense [B*H*W][pl_Cp] in the forward plane format, the A operand of the next h-half GEMM.
 struct GruEpi {
   int mode = 0;
   int Ch = 0;
@@ -53,11 +53,13 @@ struct GruEpi {
 };
 bool tma_fwd_launch_ex_eligible(const ConvP& p);
 int tma_fwd_launch_ex(ConvP& p, const TmaOperands* ops, const GruEpi* epi, cudaStream_t st);
-// split fp32 packed weights [taps][Cin][Cout] / activations into bf16 (hi, lo) planes
-int tma_split_weights(const float* w_packed, int taps, int Cin, int Cout, int CoutP, void* hi, void* lo,
+// split fp32 packed weights [taps][Cin][Cout] / activations into (hi, lo) planes; fp16 = 1: the forward format
+int tma_split_weights(const float* w_packed, int taps, int Cin, int Cout, int CoutP, int fp16, void* hi, void* lo,
                       cudaStream_t st);
-int tma_split_activations(const float* x, int N, int C, int64_t n_stride, int64_t c_stride, int pix, void* hi,
+int tma_split_activations(const float* x, int N, int C, int64_t n_stride, int64_t c_stride, int pix, int fp16, void* hi,
                           void* lo, cudaStream_t st);
+bool tma_forward_planes_fp16();   // forward operands use fp16 planes (default; options "fwd_bf16" / "oneacc" turn it off)
+int tma_saturation_count(unsigned int* count, int reset, cudaStream_t st);
 inline int tma_round64(int c) { return (c + 63) / 64 * 64; }
 // stream-ordered scratch (cudaMallocAsync pool of the engine); free with tma_scratch_free on the same stream
 int tma_scratch_alloc(void** p, size_t bytes, cudaStream_t st);

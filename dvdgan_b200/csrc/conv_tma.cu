@@ -3,14 +3,20 @@
 // Operand preparation (HBM-bound, once per conv call): the fp32 NC(D)HW activation (or dY) is split into two bf16
 // planes in channels-last layout [N][D][H][W][Cp] (ReLU / nearest-x2 upsample of the reference's F.relu /
 // F.interpolate fused in); the fp32 packed weights [tap][Cin][Cout] become [tap][CoutP][CinP] planes.
-//   x = hi + lo,  hi = bf16(x),  lo = bf16(x - hi)          (16-17 significant bits, fp32's exponent range: no
-//                                                             saturation or underflow for any finite fp32 input)
-// The GEMM issues three bf16 MMAs per algorithmic MAC,  A_hi*B_hi,  A_lo*B_hi,  A_hi*B_lo,  into fp32 TMEM accumulators:
-//   two-accumulator kernels:   D_main += A_hi*B_hi ;  D_lo += A_lo*B_hi + A_hi*B_lo ;  result = D_main + D_lo
+// Two plane formats (A and B of one tcgen05.mma must share one):
+//   fp16:  hi = fp16(x), lo = fp16((x - hi) * 2^11)   22 significant bits, |x| <= 65504.  Forward activations and
+//          weights (x_kind = 1).  Needed for the 1e-3 contract: with 16-bit-precision operands the Generator's output is
+//          1.2e-3 off the fp32 reference after 48 recurrent frames, with these 2.3e-4 (profiles/r2).  Elements beyond
+//          fp16's range are clamped AND counted (dvd_saturation_count); option "fwd_bf16" switches every launch to
+//   bf16:  hi = bf16(x), lo = bf16(x - hi)             16-17 significant bits, fp32's exponent range.  Everything that
+//          holds gradients (dgrad / wgrad operands), and the forward too under "fwd_bf16" or "oneacc".
+// The GEMM issues three MMAs per algorithmic MAC,  A_hi*B_hi,  A_lo*B_hi,  A_hi*B_lo,  into fp32 TMEM accumulators:
+//   two-accumulator kernels:   D_main += A_hi*B_hi ;  D_lo += A_lo*B_hi + A_hi*B_lo ;  result = D_main + D_lo / s
 //                              (the many small cross terms stay out of the large accumulator, whose adds truncate)
-//   ONEACC kernels:            D += all three.  Halves the TMEM footprint, which lets the persistent 256-wide CTA-pair
-//                              kernel keep TWO accumulator sets: the epilogue of tile i drains set i&1 while the MMAs of
-//                              tile i+1 fill the other one.
+//   ONEACC kernels (bf16 planes only: the low plane is unscaled):   D += all three.  Halves the TMEM footprint, which
+//                              lets the persistent 256-wide CTA-pair kernel keep TWO accumulator sets: the epilogue of
+//                              tile i drains set i&1 while the MMAs of tile i+1 fill the other one.  Measured +7..16 %
+//                              on isolated GEMMs, +2 % on the step, but tied to the bf16 planes' precision: off by default.
 //
 // forward CTA (64 + 32*EW threads): warp 0 = TMA producer (one lane), warp 1 = TMEM alloc + tcgen05.mma issuer (one
 // lane), EW = 4 or 8 epilogue warps.  A tile = 128 output pixels x 64 channels, fetched per tap as ONE 5-D TMA box
@@ -26,6 +32,7 @@
 // taps fastest in the grid so that a wave of CTAs re-uses one pixel range from L2.
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include <algorithm>
 #include <mutex>
@@ -127,9 +134,10 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
   d |= (uint64_t)2 << 61;      // SWIZZLE_128B
   return d;
 }
-// kind::f16 instruction descriptor: D = f32, A/B = bf16 (format 1), M = m, N = n; mn_major: both operands MN-major
-__device__ __forceinline__ uint32_t make_idesc(int n, int mn_major, int m) {
-  uint32_t d = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+// kind::f16 instruction descriptor: D = f32, A/B = bf16 (fmt 1) or fp16 (fmt 0), M = m, N = n; mn_major: both operands
+// MN-major
+__device__ __forceinline__ uint32_t make_idesc(int n, int mn_major, int m, uint32_t fmt = 1) {
+  uint32_t d = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
   if (mn_major) d |= (1u << 15) | (1u << 16);
   return d;
 }
@@ -186,6 +194,29 @@ __device__ __forceinline__ void bf16_split8(const float* v, uint4* hi, uint4* lo
   *lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
+// fp16 planes: hi = fp16(x), lo = fp16((x - hi) * 2^11); values beyond fp16's range are clamped and counted
+constexpr float kLoScaleFp16 = 2048.f;
+__device__ unsigned int g_fp16_saturated = 0;
+__device__ __forceinline__ void fp16_split8(const float* v, uint4* hi, uint4* lo) {
+  const float lim = 65504.f;
+  uint32_t h[4], l[4];
+  bool sat = false;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float a = v[2 * i], b = v[2 * i + 1];
+    sat = sat || fabsf(a) > lim || fabsf(b) > lim;
+    const __half2 hp = __floats2half2_rn(fminf(fmaxf(a, -lim), lim), fminf(fmaxf(b, -lim), lim));
+    const float2 hf = __half22float2(hp);
+    const float ra = (a - hf.x) * kLoScaleFp16, rb = (b - hf.y) * kLoScaleFp16;
+    const __half2 lp = __floats2half2_rn(fminf(fmaxf(ra, -lim), lim), fminf(fmaxf(rb, -lim), lim));
+    h[i] = *reinterpret_cast<const uint32_t*>(&hp);
+    l[i] = *reinterpret_cast<const uint32_t*>(&lp);
+  }
+  if (sat) atomicAdd(&g_fp16_saturated, 1u);          // rare: one count per 8-element group
+  *hi = make_uint4(h[0], h[1], h[2], h[3]);
+  *lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
 // ------------------------------------------------------------------------------------------------ operand prep
 // src: fp32, element (n, c, pix) at n1*s1 + n2*s2 + c*cs + srcpix(pix)   ->  dst planes [n][pix][Cp] bf16 hi / lo.
 // Block = 32 output pixels x 64 channels, transposed through shared memory (coalesced on both sides).
@@ -199,6 +230,7 @@ struct PrepP {
   int out_pix;       // rows per image in dst
   int W, HW, up;     // output W, H*W (for the upsample source map); up = 1: source is (H/2, W/2)
   int relu;
+  int fp16;          // plane format (see the file header)
 };
 
 __global__ void __launch_bounds__(256) prep_planes_kernel(const PrepP p) {
@@ -243,7 +275,8 @@ __global__ void __launch_bounds__(256) prep_planes_kernel(const PrepP p) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) v[i] = tile[q * 8 + i][px];
       uint4 h, l;
-      bf16_split8(v, &h, &l);
+      if (p.fp16) fp16_split8(v, &h, &l);
+      else bf16_split8(v, &h, &l);
       const int64_t o = ((int64_t)n * p.out_pix + pix) * p.Cp + c0 + q * 8;
       *reinterpret_cast<uint4*>(p.hi + o) = h;
       *reinterpret_cast<uint4*>(p.lo + o) = l;
@@ -292,9 +325,9 @@ struct Bars {
 template <int BN, bool ONEACC, int STAGES, int STAGE_BYTES, int A_BYTES, int B_BYTES, int CG>
 __device__ __forceinline__ void mma_issue_loop(uint8_t* smem, const Bars<STAGES>& bars, uint32_t main_col,
                                                uint32_t lo_col, int buf, int n_iters, int mn_major, uint32_t lbo,
-                                               uint32_t sbo, uint32_t kadv, int& stage,
-                                               uint32_t& phase /* ring position, carried across tiles */) {
-  const uint32_t idesc = make_idesc(BN, mn_major, BM * CG);
+                                               uint32_t sbo, uint32_t kadv, uint32_t fmt /* 0: fp16, 1: bf16 planes */,
+                                               int& stage, uint32_t& phase /* ring position, carried across tiles */) {
+  const uint32_t idesc = make_idesc(BN, mn_major, BM * CG, fmt);
   const int late_it = n_iters > LATE_ITERS ? n_iters - LATE_ITERS : 0;
   for (int it = 0; it < n_iters; ++it) {
     if (it == late_it) {          // tell the epilogue warps (of both CTAs of a pair) to start prefetching their operands
@@ -355,18 +388,21 @@ struct FwdP {
   ConvP c;
   TileGeom g;
   int CoutP;
+  int fp16;             // operand planes are fp16 (forward values) rather than bf16
+  float lo_inv;         // 1 / scale of the low-order planes
   GruEpi gru;           // ConvGRU gate / state epilogue (mode 0: plain conv epilogue)
   int prefetch;         // epilogue operands are prefetched into L2 late in the main loop
   int nt, tiles;        // persistent kernels: n-tiles and total (m-unit, n-tile) tiles
   int a_c_off;          // first channel of the A operand inside (shared) planes
 };
 
-// 32 consecutive channels of one pixel -> bf16 hi / lo planes (same split as prep_planes_kernel)
-__device__ __forceinline__ void store_planes32(__nv_bfloat16* hi, __nv_bfloat16* lo, const float* v) {
+// 32 consecutive channels of one pixel -> hi / lo planes (same split as prep_planes_kernel)
+__device__ __forceinline__ void store_planes32(__nv_bfloat16* hi, __nv_bfloat16* lo, const float* v, int fp16) {
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     uint4 h, l;
-    bf16_split8(v + q * 8, &h, &l);
+    if (fp16) fp16_split8(v + q * 8, &h, &l);
+    else bf16_split8(v + q * 8, &h, &l);
     reinterpret_cast<uint4*>(hi)[q] = h;
     reinterpret_cast<uint4*>(lo)[q] = l;
   }
@@ -498,7 +534,8 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
         const uint32_t main_col = tmem_base + (uint32_t)(buf * C::SET_COLS);
         // K-major operands: LBO unused (16), SBO = 1024 (8 rows of 128 B), 32 bytes (2 units) per UMMA_K step
         mma_issue_loop<BN, ONEACC, C::STAGES, C::STAGE_BYTES, C::A_BYTES, C::B_BYTES, CG>(
-            smem, bars, main_col, ONEACC ? main_col : main_col + BN, buf, n_iters, 0, 16, 1024, 2, stage, phase);
+            smem, bars, main_col, ONEACC ? main_col : main_col + BN, buf, n_iters, 0, 16, 1024, 2, fp.fp16 ? 0u : 1u,
+            stage, phase);
       }
     }
     __syncwarp();
@@ -573,7 +610,7 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
         for (int j = 0; j < 32; ++j) ge.out2[(int64_t)nb * ge.o2_s1 + (int64_t)(c0 + j) * p.DHW + pix] = o2[j];
         if (ge.pl_hi)
           store_planes32(reinterpret_cast<__nv_bfloat16*>(ge.pl_hi) + (int64_t)m * ge.pl_Cp + c0,
-                         reinterpret_cast<__nv_bfloat16*>(ge.pl_lo) + (int64_t)m * ge.pl_Cp + c0, o2);
+                         reinterpret_cast<__nv_bfloat16*>(ge.pl_lo) + (int64_t)m * ge.pl_Cp + c0, o2, fp.fp16);
       }
     };
     auto emit32 = [&](int cb, const float* v) {
@@ -651,7 +688,7 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
         tmem_ld32(taddr + BN + cb, r1);
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r0[j]) + __uint_as_float(r1[j]);
+        for (int j = 0; j < 32; ++j) v[j] = fmaf(__uint_as_float(r1[j]), fp.lo_inv, __uint_as_float(r0[j]));
       }
       if (!ok) continue;
       emit32(cb, v);
@@ -808,7 +845,7 @@ conv_tma_wgrad_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_c
       int stage = 0;
       uint32_t phase = 0;
       mma_issue_loop<BN, false, C::STAGES, C::STAGE_BYTES, C::A_BYTES, C::B_BYTES, CG>(
-          smem, bars, tmem_base, tmem_base + BN, 0, n_iters, 1, 8192, 1024, 128, stage, phase);
+          smem, bars, tmem_base, tmem_base + BN, 0, n_iters, 1, 8192, 1024, 128, 1u, stage, phase);
     }
     __syncwarp();
   } else {
@@ -951,11 +988,11 @@ struct Scratch {
 };
 
 static int prep_planes(const float* src, int N1, int N2, int C, int Cp, int64_t s1, int64_t s2, int64_t cs, int in_pix,
-                       int out_pix, int W, int HW, int up, int relu, __nv_bfloat16* hi, __nv_bfloat16* lo,
+                       int out_pix, int W, int HW, int up, int relu, int fp16, __nv_bfloat16* hi, __nv_bfloat16* lo,
                        cudaStream_t st) {
   PrepP p;
   p.src = src; p.hi = hi; p.lo = lo; p.N2 = N2; p.C = C; p.Cp = Cp; p.s1 = s1; p.s2 = s2; p.cs = cs;
-  p.in_pix = in_pix; p.out_pix = out_pix; p.W = W; p.HW = HW; p.up = up; p.relu = relu;
+  p.in_pix = in_pix; p.out_pix = out_pix; p.W = W; p.HW = HW; p.up = up; p.relu = relu; p.fp16 = fp16;
   const int N = N1 * N2;
   DVD_CHECK_ARG(N <= 65535);          // gridDim.z
   dim3 grid(ceil_div(out_pix, 32), Cp / 64, N);
@@ -1042,15 +1079,18 @@ bool tma_fwd_eligible(const ConvP& p) {
 int tma_fwd_launch(ConvP& p, cudaStream_t st) { return tma_fwd_launch_ex(p, nullptr, nullptr, st); }
 bool tma_fwd_launch_ex_eligible(const ConvP& p) { return tma_fwd_eligible(p); }
 
-int tma_split_weights(const float* w_packed, int taps, int Cin, int Cout, int CoutP, void* hi, void* lo,
+// forward operands (x_kind = 1) are split into fp16 planes unless "fwd_bf16" / "oneacc" ask for bf16 everywhere
+bool tma_forward_planes_fp16() { return !get_option(OPT_FWD_BF16) && !get_option(OPT_ONEACC); }
+
+int tma_split_weights(const float* w_packed, int taps, int Cin, int Cout, int CoutP, int fp16, void* hi, void* lo,
                       cudaStream_t st) {
   // [tap][Cin][Cout] fp32 -> [tap][CoutP][CinP]   (image = tap, channel = cin, pixel = cout)
   return tma::prep_planes(w_packed, taps, 1, Cin, tma_round64(Cin), (int64_t)Cin * Cout, 0, Cout, Cout, CoutP, 1, 1, 0,
-                          0, reinterpret_cast<__nv_bfloat16*>(hi), reinterpret_cast<__nv_bfloat16*>(lo), st);
+                          0, fp16, reinterpret_cast<__nv_bfloat16*>(hi), reinterpret_cast<__nv_bfloat16*>(lo), st);
 }
-int tma_split_activations(const float* x, int N, int C, int64_t n_stride, int64_t c_stride, int pix, void* hi, void* lo,
-                          cudaStream_t st) {
-  return tma::prep_planes(x, N, 1, C, tma_round64(C), n_stride, 0, c_stride, pix, pix, 1, 1, 0, 0,
+int tma_split_activations(const float* x, int N, int C, int64_t n_stride, int64_t c_stride, int pix, int fp16, void* hi,
+                          void* lo, cudaStream_t st) {
+  return tma::prep_planes(x, N, 1, C, tma_round64(C), n_stride, 0, c_stride, pix, pix, 1, 1, 0, 0, fp16,
                           reinterpret_cast<__nv_bfloat16*>(hi), reinterpret_cast<__nv_bfloat16*>(lo), st);
 }
 
@@ -1076,6 +1116,8 @@ int tma_fwd_launch_ex(ConvP& p, const TmaOperands* ops, const GruEpi* epi, cudaS
   if (epi) fp.gru = *epi;
   fp.prefetch = get_option(OPT_EPI_PREFETCH);
   if (fp.gru.mode) DVD_CHECK_ARG(d.accumulate && fp.gru.Ch % 32 == 0 && !d.out_act && !p.res && !p.bias);
+  fp.fp16 = (d.x_kind == 1 && tma_forward_planes_fp16()) ? 1 : 0;
+  fp.lo_inv = fp.fp16 ? 1.f / kLoScaleFp16 : 1.f;
   const int64_t ctas = (int64_t)mt * ceil_div(d.Cout, bn);
   int nsplit = 1;
   if (ctas < nsm && d.out_act == 0 && p.iters_total >= 8 && !fp.gru.mode) {
@@ -1107,7 +1149,7 @@ int tma_fwd_launch_ex(ConvP& p, const TmaOperands* ops, const GruEpi* epi, cudaS
   } else {
     __nv_bfloat16* h = cur; __nv_bfloat16* l = cur + a_elems; cur += 2 * a_elems;
     DVD_TRY(prep_planes(p.x, d.N1, d.N2, d.Cin, CinP, d.x_s1, d.x_s2, d.x_cs, p.DHW, p.DHW, d.W, p.HW, d.in_up,
-                        d.in_relu, h, l, st));
+                        d.in_relu, fp.fp16, h, l, st));
     a_hi = h; a_lo = l;
   }
   if (ext_w) {
@@ -1117,7 +1159,7 @@ int tma_fwd_launch_ex(ConvP& p, const TmaOperands* ops, const GruEpi* epi, cudaS
     __nv_bfloat16* h = cur; __nv_bfloat16* l = cur + w_elems;
     // weights: [tap][Cin][Cout] fp32 -> [tap][CoutP][CinP]   (image = tap, channel = cin, pixel = cout)
     DVD_TRY(prep_planes(p.w, p.taps, 1, d.Cin, CinP, (int64_t)d.Cin * d.Cout, 0, d.Cout, d.Cout, CoutP, 1, 1, 0, 0,
-                        h, l, st));
+                        fp.fp16, h, l, st));
     w_hi = h; w_lo = l;
   }
   CUtensorMap maps[4];
@@ -1137,7 +1179,7 @@ int tma_fwd_launch_ex(ConvP& p, const TmaOperands* ops, const GruEpi* epi, cudaS
   fp.nt = ceil_div(d.Cout, bn);
   fp.tiles = (mt / (pair ? 2 : 1)) * fp.nt;
   const bool persist = get_option(OPT_PERSIST) && pair && nsplit == 1 && bn >= 128 && fp.tiles > nsm / 2;
-  const bool oneacc = persist && get_option(OPT_ONEACC);
+  const bool oneacc = persist && get_option(OPT_ONEACC) && !fp.fp16;
   // short reductions on narrow tiles: two CTAs per SM
   const bool occ2 = get_option(OPT_OCC2) && !fp.gru.mode && bn <= 128 && p.iters_total <= 40 &&
                     ctas >= 2 * (int64_t)nsm && (pair || bn == 64);     // (one CTA, 128 wide) stages are 64 KB: no room
@@ -1195,7 +1237,18 @@ void tma_scratch_free(void* p, cudaStream_t st) {
 }
 int tma_split_gradients(const float* g, int N, int C, int64_t n_stride, int64_t c_stride, int pix, void* hi, void* lo,
                         cudaStream_t st) {
-  return tma_split_activations(g, N, C, n_stride, c_stride, pix, hi, lo, st);
+  return tma_split_activations(g, N, C, n_stride, c_stride, pix, 0, hi, lo, st);
+}
+
+// groups of 8 operand elements that were clamped to fp16's range since the last reset (current device); synchronises
+int tma_saturation_count(unsigned int* count, int reset, cudaStream_t st) {
+  DVD_CUDA(cudaMemcpyFromSymbolAsync(count, tma::g_fp16_saturated, sizeof(unsigned int), 0, cudaMemcpyDeviceToHost, st));
+  if (reset) {
+    const unsigned int zero = 0;
+    DVD_CUDA(cudaMemcpyToSymbolAsync(tma::g_fp16_saturated, &zero, sizeof(unsigned int), 0, cudaMemcpyHostToDevice, st));
+  }
+  DVD_CUDA(cudaStreamSynchronize(st));
+  return 0;
 }
 int tma_wgrad_launch(ConvP& p, float* dwp, cudaStream_t st) { return tma_wgrad_launch_ex(p, dwp, nullptr, st); }
 // shared dY planes need whole images per 64-pixel box unless they map one to one
@@ -1247,7 +1300,7 @@ int tma_wgrad_launch_ex(ConvP& p, float* dwp, const TmaWgOperands* ops, cudaStre
   __nv_bfloat16* x_lo = x_hi + x_elems;
   const __nv_bfloat16 *y_hi, *y_lo;
   DVD_TRY(prep_planes(p.x, d.N1, d.N2, d.Cin, CinP, d.x_s1, d.x_s2, d.x_cs, p.DHW, p.DHW, d.W, p.HW, 0, d.in_relu,
-                      x_hi, x_lo, st));
+                      0, x_hi, x_lo, st));
   int y_images = N;
   wp.y_c_off = 0; wp.y_T = 0; wp.y_t_off = 0; wp.y_n2 = d.N2;
   if (ext_y) {
@@ -1258,7 +1311,7 @@ int tma_wgrad_launch_ex(ConvP& p, float* dwp, const TmaWgOperands* ops, cudaStre
     if (!(ops->y_T == d.N2 && ops->y_t_off == 0)) { wp.y_T = ops->y_T; wp.y_t_off = ops->y_t_off; }
   } else {
     __nv_bfloat16* h = x_lo + x_elems; __nv_bfloat16* l = h + y_elems;
-    DVD_TRY(prep_planes(p.y, d.N1, d.N2, d.Cout, CoutP, d.y_s1, d.y_s2, d.y_cs, p.DHW, p.DHW, d.W, p.HW, 0, 0, h, l, st));
+    DVD_TRY(prep_planes(p.y, d.N1, d.N2, d.Cout, CoutP, d.y_s1, d.y_s2, d.y_cs, p.DHW, p.DHW, d.W, p.HW, 0, 0, 0, h, l, st));
     y_hi = h; y_lo = l;
   }
   CUtensorMap maps[4];

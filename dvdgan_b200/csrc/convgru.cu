@@ -206,7 +206,7 @@ struct GruWs {
   float *dwx, *dwhur, *dwho;            // packed weight grads
   float *d_rh, *carry0, *carry1, *dbias;
   double* dscratch;
-  // fused forward path: bf16 hi/lo planes of the h-half weights and of the per-step GEMM inputs
+  // fused forward path: hi/lo planes (forward format) of the h-half weights and of the per-step GEMM inputs
   uint16_t *whur_hi, *whur_lo, *who_hi, *who_lo;      // [taps][CoutP][ChP]
   uint16_t *hpl_hi[2], *hpl_lo[2];                    // planes of h_{t-1} / h_t (ping-pong), [B*HW][ChP]
   uint16_t *rhpl_hi, *rhpl_lo;                        // planes of r * h_{t-1}
@@ -302,7 +302,7 @@ extern "C" int dvd_convgru_layer_fwd(const float* x, int64_t x_bs, int64_t x_ts,
   }
   const int eb = ew_blocks((int64_t)B * chw);
   // Fused path: the two h-half GEMMs of a step run on the TMA/tcgen05 engine with the gate math in their epilogues
-  // (update|reset: sigmoid, r*h;  out: tanh, state update) which also emit the bf16 planes the next GEMM reads, and the
+  // (update|reset: sigmoid, r*h;  out: tanh, state update) which also emit the operand planes the next GEMM reads, and the
   // h-half weight planes are split once per layer instead of once per step.
   dvd_conv_desc d_ur = base_desc(B, 1, Ch, 2 * Ch, H, W, k), d_o = base_desc(B, 1, Ch, Ch, H, W, k);
   d_ur.x_kind = d_o.x_kind = 1; d_ur.accumulate = d_o.accumulate = 1;
@@ -310,9 +310,10 @@ extern "C" int dvd_convgru_layer_fwd(const float* x, int64_t x_bs, int64_t x_ts,
   const int ChP = tma_round64(Ch), Co2P = tma_round64(2 * Ch);
   const bool fused = gru_fused_enabled() && T > 1 && Ch % 32 == 0 && conv_fwd_ex_eligible(&d_ur) &&
                      conv_fwd_ex_eligible(&d_o);
+  const int f16 = tma_forward_planes_fp16() ? 1 : 0;       // the epilogues write the step-to-step planes in this format
   if (fused) {
-    DVD_TRY(tma_split_weights(ws.whur, taps, Ch, 2 * Ch, Co2P, ws.whur_hi, ws.whur_lo, st));
-    DVD_TRY(tma_split_weights(ws.who, taps, Ch, Ch, ChP, ws.who_hi, ws.who_lo, st));
+    DVD_TRY(tma_split_weights(ws.whur, taps, Ch, 2 * Ch, Co2P, f16, ws.whur_hi, ws.whur_lo, st));
+    DVD_TRY(tma_split_weights(ws.who, taps, Ch, Ch, ChP, f16, ws.who_hi, ws.who_lo, st));
     if (ChP != Ch) {      // padded channels of the planes the epilogues write stay zero
       const size_t pl = (size_t)B * HW * ChP * sizeof(uint16_t);
       for (int i = 0; i < 2; ++i) {
@@ -332,7 +333,7 @@ extern "C" int dvd_convgru_layer_fwd(const float* x, int64_t x_bs, int64_t x_ts,
     if (fused && hp) {
       const int sp = (t + 1) & 1, sn = t & 1;          // slots of h_{t-1} and h_t
       if (!have_planes)
-        DVD_TRY(tma_split_activations(hp, B, Ch, hp_bs, HW, HW, ws.hpl_hi[sp], ws.hpl_lo[sp], st));
+        DVD_TRY(tma_split_activations(hp, B, Ch, hp_bs, HW, HW, f16, ws.hpl_hi[sp], ws.hpl_lo[sp], st));
       TmaOperands op;
       GruEpi ge;
       op.a_hi = ws.hpl_hi[sp]; op.a_lo = ws.hpl_lo[sp]; op.w_hi = ws.whur_hi; op.w_lo = ws.whur_lo; op.CoutP = Co2P;
@@ -397,8 +398,8 @@ extern "C" int dvd_convgru_layer_bwd(const float* x, int64_t x_bs, int64_t x_ts,
   const int ChP = tma_round64(Ch), Co2P = tma_round64(2 * Ch);
   const bool wplanes = gru_fused_enabled() && T > 1 && conv_fwd_ex_eligible(&d_rh) && conv_fwd_ex_eligible(&d_hp);
   if (wplanes) {
-    DVD_TRY(tma_split_weights(ws.whoT, taps, Ch, Ch, ChP, ws.whoT_hi, ws.whoT_lo, st));
-    DVD_TRY(tma_split_weights(ws.whurT, taps, 2 * Ch, Ch, ChP, ws.whurT_hi, ws.whurT_lo, st));
+    DVD_TRY(tma_split_weights(ws.whoT, taps, Ch, Ch, ChP, 0, ws.whoT_hi, ws.whoT_lo, st));
+    DVD_TRY(tma_split_weights(ws.whurT, taps, 2 * Ch, Ch, ChP, 0, ws.whurT_hi, ws.whurT_lo, st));
   }
   // The pre-activation gradients (da_u | da_r | da_o) of all frames feed four GEMMs (x-dgrad and the three weight
   // gradients): split them into bf16 planes ONCE and hand the planes to all four (channel / frame offsets in the

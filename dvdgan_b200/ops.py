@@ -189,6 +189,63 @@ def fork(x, n=2):
     return Fork.apply(x, n)
 
 
+def _conv_forward(x, w, bias, u, v, res, in_relu, in_up, out_act, res_up):
+    """Shared forward of ConvFn / CBNConvFn: (optional) power iteration, weight packing with 1/sigma folded in, the
+    conv itself.  Returns (y, sigma)."""
+    sn = u is not None
+    sigma = sn_sigma(w, u, v) if sn else None
+    k = _ksize(w)
+    wp = pack_weight(w, sigma)
+    lin = x.dim() == 2
+    xin = x.view(x.shape[0], x.shape[1], 1, 1) if lin else x
+    rin = _c(res) if res is not None else None
+    y = conv_raw(xin, wp, bias, w.shape[0], k, in_relu=in_relu, in_up=in_up, out_act=out_act, res=rin, res_up=res_up,
+                 x_kind=1)
+    if lin:
+        y = y.view(y.shape[0], y.shape[1])
+    return y, sigma
+
+
+def _conv_backward(x, w, sigma, u, v, y, dy, cfg, need_x, need_w, need_b, need_res):
+    """Shared backward: (dx, dw, db, dres) of a conv whose input was x (before the fused ReLU / upsample)."""
+    in_relu, in_up, out_act, res_up, k, lin, has_bias, has_res = cfg
+    dy = _c(dy)
+    if out_act:
+        d2 = _new(dy.shape, dy)
+        call("dvd_act_bwd", ptr(y), ptr(dy), dy.numel(), out_act, ptr(d2))
+        dy = d2
+    xin = x.view(x.shape[0], x.shape[1], 1, 1) if lin else x
+    dyin = dy.view(dy.shape[0], dy.shape[1], 1, 1) if lin else dy
+    Co = w.shape[0]
+    dx = dw = db = dres = None
+    if need_w:
+        g = unpack_wgrad(wgrad_raw(xin, dyin, k, in_relu=in_relu, in_up=in_up), w)
+        dw = sn_backward(g, w, u, v, sigma) if sigma is not None else g
+    if has_bias and need_b:
+        db = channel_sum(dyin, Co)
+    if need_x:
+        wpt = pack_weight(w, sigma, transpose=True)
+        if in_up:
+            full = conv_raw(dyin, wpt, None, w.shape[1], k)
+            N, Ci, D, H, W = _spatial(full)
+            dx = _new(xin.shape, xin)
+            call("dvd_avgpool_fwd", ptr(full), N * Ci * D, 1, H, W, 1, 2, 2, 4.0, 0, ptr(dx))
+        else:
+            dx = conv_raw(dyin, wpt, None, w.shape[1], k)
+        if in_relu:
+            call("dvd_act_bwd", ptr(xin), ptr(dx), dx.numel(), 1, ptr(dx))
+        dx = dx.view(x.shape)
+    if has_res and need_res:
+        if res_up:
+            N, C, D, H, W = _spatial(dyin)
+            shape = (N, C, H // 2, W // 2) if dyin.dim() == 4 else (N, C, D, H // 2, W // 2)
+            dres = _new(shape, dy)
+            call("dvd_avgpool_fwd", ptr(dyin), N * C * D, 1, H, W, 1, 2, 2, 4.0, 0, ptr(dres))
+        else:
+            dres = dy
+    return dx, dw, db, dres
+
+
 class ConvFn(torch.autograd.Function):
     """Stride-1 same-padded conv (2-D/3-D) or Linear, optionally spectrally normalised, with fused
     input ReLU / nearest x2 upsample, bias, (upsampled) residual add and output activation.
@@ -200,61 +257,16 @@ class ConvFn(torch.autograd.Function):
     def forward(ctx, x, w, bias, u, v, res, in_relu, in_up, out_act, res_up):
         _C.require_cuda(x, w)
         x = _c(x)
-        sn = u is not None
-        sigma = sn_sigma(w, u, v) if sn else None
-        k = _ksize(w)
-        wp = pack_weight(w, sigma)
-        lin = x.dim() == 2
-        xin = x.view(x.shape[0], x.shape[1], 1, 1) if lin else x
-        rin = None
-        if res is not None:
-            rin = _c(res)
-        y = conv_raw(xin, wp, bias, w.shape[0], k, in_relu=in_relu, in_up=in_up, out_act=out_act, res=rin,
-                     res_up=res_up, x_kind=1)
-        if lin:
-            y = y.view(y.shape[0], y.shape[1])
-        ctx.save_for_backward(x, w, sigma if sn else None, u, v, y if out_act else None)
-        ctx.cfg = (in_relu, in_up, out_act, res_up, k, lin, bias is not None, res is not None)
+        y, sigma = _conv_forward(x, w, bias, u, v, res, in_relu, in_up, out_act, res_up)
+        ctx.save_for_backward(x, w, sigma, u, v, y if out_act else None)
+        ctx.cfg = (in_relu, in_up, out_act, res_up, _ksize(w), x.dim() == 2, bias is not None, res is not None)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         x, w, sigma, u, v, y = ctx.saved_tensors
-        in_relu, in_up, out_act, res_up, k, lin, has_bias, has_res = ctx.cfg
-        dy = _c(dy)
-        if out_act:
-            d2 = _new(dy.shape, dy)
-            call("dvd_act_bwd", ptr(y), ptr(dy), dy.numel(), out_act, ptr(d2))
-            dy = d2
-        xin = x.view(x.shape[0], x.shape[1], 1, 1) if lin else x
-        dyin = dy.view(dy.shape[0], dy.shape[1], 1, 1) if lin else dy
-        Co = w.shape[0]
-        dx = dw = db = dres = None
-        if ctx.needs_input_grad[1]:
-            g = unpack_wgrad(wgrad_raw(xin, dyin, k, in_relu=in_relu, in_up=in_up), w)
-            dw = sn_backward(g, w, u, v, sigma) if sigma is not None else g
-        if has_bias and ctx.needs_input_grad[2]:
-            db = channel_sum(dyin, Co)
-        if ctx.needs_input_grad[0]:
-            wpt = pack_weight(w, sigma, transpose=True)
-            if in_up:
-                full = conv_raw(dyin, wpt, None, w.shape[1], k)
-                N, Ci, D, H, W = _spatial(full)
-                dx = _new(xin.shape, xin)
-                call("dvd_avgpool_fwd", ptr(full), N * Ci * D, 1, H, W, 1, 2, 2, 4.0, 0, ptr(dx))
-            else:
-                dx = conv_raw(dyin, wpt, None, w.shape[1], k)
-            if in_relu:
-                call("dvd_act_bwd", ptr(xin), ptr(dx), dx.numel(), 1, ptr(dx))
-            dx = dx.view(x.shape)
-        if has_res and ctx.needs_input_grad[5]:
-            if res_up:
-                N, C, D, H, W = _spatial(dyin)
-                shape = (N, C, H // 2, W // 2) if dyin.dim() == 4 else (N, C, D, H // 2, W // 2)
-                dres = _new(shape, dy)
-                call("dvd_avgpool_fwd", ptr(dyin), N * C * D, 1, H, W, 1, 2, 2, 4.0, 0, ptr(dres))
-            else:
-                dres = dy
+        dx, dw, db, dres = _conv_backward(x, w, sigma, u, v, y, dy, ctx.cfg, ctx.needs_input_grad[0],
+                                          ctx.needs_input_grad[1], ctx.needs_input_grad[2], ctx.needs_input_grad[5])
         return dx, dw, db, None, None, dres, None, None, None, None
 
 
@@ -283,6 +295,33 @@ class SNWeightFn(torch.autograd.Function):
         return sn_backward(_c(g), w, u, v, sigma), None, None
 
 
+def _cbn_stats(x, running_mean, running_var, nbt, training, momentum, eps):
+    N, C, H, W = x.shape
+    mean, rstd = _new((C,), x), _new((C,), x)
+    scratch = torch.empty(2 * C, device=x.device, dtype=torch.float64)
+    call("dvd_bn_stats", ptr(x), N, C, H * W, int(training), momentum, eps, ptr(running_mean), ptr(running_var),
+         ptr(nbt), ptr(mean), ptr(rstd), ptr(scratch))
+    return mean, rstd
+
+
+def _cbn_apply(x, gb, mean, rstd, relu, up):
+    N, C, H, W = x.shape
+    y = _new((N, C, H << up, W << up), x)
+    call("dvd_cbn_apply", ptr(x), ptr(gb), gb.shape[0], ptr(mean), ptr(rstd), N, C, H, W, int(relu), up, ptr(y))
+    return y
+
+
+def _cbn_backward(x, gb, mean, rstd, dy, relu, up, training):
+    N, C, H, W = x.shape
+    dy = _c(dy)
+    dx = _new(x.shape, x)
+    dgb = _new(gb.shape, gb)
+    scratch = _new((2 * C,), x)
+    call("dvd_cbn_bwd", ptr(x), ptr(gb), gb.shape[0], ptr(mean), ptr(rstd), ptr(dy), N, C, H, W, int(relu), up,
+         int(training), ptr(dx), ptr(dgb), ptr(scratch))
+    return dx, dgb
+
+
 class CBNFn(torch.autograd.Function):
     """BatchNorm2d(affine=False) + per-row (gamma|beta) affine + optional ReLU + optional nearest x2
     upsample (Normalization.py:78-88, GResBlock.py:49-55)."""
@@ -291,14 +330,8 @@ class CBNFn(torch.autograd.Function):
     def forward(ctx, x, gb, running_mean, running_var, nbt, relu, up, training, momentum, eps):
         _C.require_cuda(x, gb)
         x, gb = _c(x), _c(gb)
-        N, C, H, W = x.shape
-        R = gb.shape[0]
-        mean, rstd = _new((C,), x), _new((C,), x)
-        scratch = torch.empty(2 * C, device=x.device, dtype=torch.float64)
-        call("dvd_bn_stats", ptr(x), N, C, H * W, int(training), momentum, eps, ptr(running_mean), ptr(running_var),
-             ptr(nbt), ptr(mean), ptr(rstd), ptr(scratch))
-        y = _new((N, C, H << up, W << up), x)
-        call("dvd_cbn_apply", ptr(x), ptr(gb), R, ptr(mean), ptr(rstd), N, C, H, W, int(relu), up, ptr(y))
+        mean, rstd = _cbn_stats(x, running_mean, running_var, nbt, training, momentum, eps)
+        y = _cbn_apply(x, gb, mean, rstd, relu, up)
         ctx.save_for_backward(x, gb, mean, rstd)
         ctx.cfg = (relu, up, training)
         return y
@@ -307,15 +340,41 @@ class CBNFn(torch.autograd.Function):
     def backward(ctx, dy):
         x, gb, mean, rstd = ctx.saved_tensors
         relu, up, training = ctx.cfg
-        N, C, H, W = x.shape
-        R = gb.shape[0]
-        dy = _c(dy)
-        dx = _new(x.shape, x)
-        dgb = _new(gb.shape, gb)
-        scratch = _new((2 * C,), x)
-        call("dvd_cbn_bwd", ptr(x), ptr(gb), R, ptr(mean), ptr(rstd), ptr(dy), N, C, H, W, int(relu), up,
-             int(training), ptr(dx), ptr(dgb), ptr(scratch))
+        dx, dgb = _cbn_backward(x, gb, mean, rstd, dy, relu, up, training)
         return dx, dgb, None, None, None, None, None, None, None, None
+
+
+class CBNConvFn(torch.autograd.Function):
+    """ConditionalNorm -> ReLU -> [nearest x2] -> SN-conv (+ residual) as ONE autograd node (GResBlock.py:49-57, 59-64).
+    Same kernels as CBNFn followed by ConvFn; the difference is what is kept for the backward: only the block's
+    pre-normalisation input x (and the per-channel statistics).  The normalised / rectified / upsampled activation --
+    up to 4x the size of x and 61 % of what a GResBlock used to save -- is transient in the forward and recomputed by
+    one more dvd_cbn_apply (an HBM-speed pass) at the start of the backward."""
+
+    @staticmethod
+    def forward(ctx, x, gb, running_mean, running_var, nbt, up, training, momentum, eps, w, bias, u, v, res, res_up):
+        _C.require_cuda(x, gb, w)
+        x, gb = _c(x), _c(gb)
+        mean, rstd = _cbn_stats(x, running_mean, running_var, nbt, training, momentum, eps)
+        a = _cbn_apply(x, gb, mean, rstd, True, up)
+        y, sigma = _conv_forward(a, w, bias, u, v, res, 0, 0, 0, res_up)
+        del a
+        ctx.save_for_backward(x, gb, mean, rstd, w, sigma, u, v)
+        ctx.cfg = (up, training, (0, 0, 0, res_up, _ksize(w), False, bias is not None, res is not None))
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, gb, mean, rstd, w, sigma, u, v = ctx.saved_tensors
+        up, training, ccfg = ctx.cfg
+        a = _cbn_apply(x, gb, mean, rstd, True, up)                  # recompute the conv's input
+        ni = ctx.needs_input_grad
+        da, dw, db, dres = _conv_backward(a, w, sigma, u, v, None, dy, ccfg, ni[0] or ni[1], ni[9], ni[10], ni[13])
+        del a
+        dx = dgb = None
+        if da is not None:
+            dx, dgb = _cbn_backward(x, gb, mean, rstd, da, True, up, training)
+        return dx, dgb, None, None, None, None, None, None, None, dw, db, None, None, dres, None
 
 
 # ConvGRU BPTT state policy.  False: keep the activated gates (3Ch) and r*h (Ch) of every frame next to h (Ch) -- 20
@@ -345,10 +404,11 @@ class GRULayerFn(torch.autograd.Function):
     x: (B,T,Cx,H,W), or (B,Cx,H,W) fed to every frame (Generator.py:88-92, Q13) when T_bcast > 0."""
 
     @staticmethod
-    def _run_fwd(x, h0, wu, wr, wo, bu, br, bo, cfg):
+    def _run_fwd(x, h0, wu, wr, wo, bu, br, bo, cfg, h=None):
         B, T, Cx, Ch, H, W, k, x_bs, x_ts, _ = cfg
         gates = _new((B, T, 3 * Ch, H, W), x)
-        h = _new((B, T, Ch, H, W), x)
+        if h is None:
+            h = _new((B, T, Ch, H, W), x)
         rh = _new((B, T, Ch, H, W), x)
         nbytes = _C.lib().dvd_convgru_layer_workspace_bytes(B, T, Cx, Ch, H, W, k)
         ws = torch.empty(nbytes, device=x.device, dtype=torch.uint8)
@@ -390,7 +450,8 @@ class GRULayerFn(torch.autograd.Function):
         B, T, Cx, Ch, H, W, k, x_bs, x_ts, T_bcast = ctx.cfg
         if ctx.lean:
             x, h0, wu, wr, wo, bu, br, bo, h = ctx.saved_tensors
-            gates, _, rh = GRULayerFn._run_fwd(x, h0, wu, wr, wo, bu, br, bo, ctx.cfg)
+            # the recomputation rewrites the kept h with the values it already holds (same kernels, same operands)
+            gates, _, rh = GRULayerFn._run_fwd(x, h0, wu, wr, wo, bu, br, bo, ctx.cfg, h=h)
         else:
             x, h0, wu, wr, wo, gates, h, rh = ctx.saved_tensors
         dh = _c(dh)
@@ -463,7 +524,11 @@ class MaxPoolFn(torch.autograd.Function):
 
 class AttnCoreFn(torch.autograd.Function):
     """softmax(Q^T K) applied to V (Discriminators.py:108-114; Attention.py:92-101,165-176).
-    q (B,dq,Nq) [or (B,Nq,dq) if q_token_major], k (B,dq,Nk), v (B,dv,Nk) -> (B,dv,Nq)."""
+    q (B,dq,Nq) [or (B,Nq,dq) if q_token_major], k (B,dq,Nk), v (B,dv,Nk) -> (B,dv,Nq).
+
+    Channel-major shapes the tensor-core kernel covers (dvd_attn_flash_supported) never materialise the (B,Nq,Nk) map:
+    the forward keeps the log-sum-exp per query and the backward recomputes the probabilities from it.  The rest
+    (SeparableAttnCell's raw-view token-major q, odd token counts) runs the materialised path."""
 
     @staticmethod
     def forward(ctx, q, k, v, q_token_major):
@@ -472,19 +537,46 @@ class AttnCoreFn(torch.autograd.Function):
         B = q.shape[0]
         Nq, dq = (q.shape[1], q.shape[2]) if q_token_major else (q.shape[2], q.shape[1])
         dv, Nk = v.shape[1], v.shape[2]
-        attn = _new((B, Nq, Nk), q)
         out = _new((B, dv, Nq), q)
+        lib = _C.lib()
+        ctx.cfg = (B, dq, dv, Nq, Nk, q_token_major)
+        ctx.flash = (not q_token_major) and bool(lib.dvd_attn_flash_supported(B, dq, dv, Nq, Nk, 0))
+        if ctx.flash:
+            lse = _new((B, Nq), q)
+            nbytes = lib.dvd_attn_flash_workspace_bytes(B, dq, dv, Nq, Nk, 0)
+            ws = torch.empty(nbytes, device=q.device, dtype=torch.uint8)
+            call("dvd_attn_flash_fwd", ptr(q), dq * Nq, ptr(k), dq * Nk, ptr(v), dv * Nk, ptr(out), dv * Nq, ptr(lse),
+                 B, dq, dv, Nq, Nk, ptr(ws), nbytes)
+            ctx.save_for_backward(q, k, v, out, lse)
+            return out
+        attn = _new((B, Nq, Nk), q)
         call("dvd_attn_fwd", ptr(q), dq * Nq, ptr(k), dq * Nk, ptr(v), dv * Nk, ptr(attn), ptr(out), dv * Nq, B, dq,
              dv, Nq, Nk, int(q_token_major))
         ctx.save_for_backward(q, k, v, attn)
-        ctx.cfg = (B, dq, dv, Nq, Nk, q_token_major)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        q, k, v, attn = ctx.saved_tensors
         B, dq, dv, Nq, Nk, qtm = ctx.cfg
         dout = _c(dout)
+        lib = _C.lib()
+        if ctx.flash and lib.dvd_attn_flash_supported(B, dq, dv, Nq, Nk, 1):
+            q, k, v, out, lse = ctx.saved_tensors
+            dq_, dk_, dv_ = _new(q.shape, q), _new(k.shape, q), _new(v.shape, q)
+            nbytes = lib.dvd_attn_flash_workspace_bytes(B, dq, dv, Nq, Nk, 1)
+            ws = torch.empty(nbytes, device=q.device, dtype=torch.uint8)
+            call("dvd_attn_flash_bwd", ptr(q), dq * Nq, ptr(k), dq * Nk, ptr(v), dv * Nk, ptr(out), dv * Nq, ptr(dout),
+                 dv * Nq, ptr(lse), ptr(dq_), dq * Nq, ptr(dk_), dq * Nk, ptr(dv_), dv * Nk, B, dq, dv, Nq, Nk,
+                 ptr(ws), nbytes)
+            return dq_, dk_, dv_, None
+        if ctx.flash:       # forward on the tensor cores, backward shape outside their coverage (dv > 128): rebuild the map
+            q, k, v, _, _ = ctx.saved_tensors
+            attn = _new((B, Nq, Nk), q)
+            scratch_out = _new((B, dv, Nq), q)
+            call("dvd_attn_fwd", ptr(q), dq * Nq, ptr(k), dq * Nk, ptr(v), dv * Nk, ptr(attn), ptr(scratch_out), dv * Nq,
+                 B, dq, dv, Nq, Nk, 0)
+        else:
+            q, k, v, attn = ctx.saved_tensors
         dattn = _new(attn.shape, attn)
         dq_, dk_, dv_ = _new(q.shape, q), _new(k.shape, q), _new(v.shape, q)
         call("dvd_attn_bwd", ptr(q), dq * Nq, ptr(k), dq * Nk, ptr(v), dv * Nk, ptr(attn), ptr(dattn), ptr(dout),

@@ -23,7 +23,7 @@ import time
 import torch
 import torch.distributed as dist
 
-from . import ops
+from . import _C, ops
 from .Module.Discriminators import SpatialDiscriminator, TemporalDiscriminator
 from .Module.Generator import Generator
 from .utils import denorm, sample_k_frames, vid_downsample
@@ -315,6 +315,23 @@ class Trainer(object):
         return {"ds_loss": ds_loss.detach(), "dt_loss": dt_loss.detach(), "g_loss": g_loss.detach(),
                 "g_s_loss": g_s_loss.detach(), "g_t_loss": g_t_loss.detach()}
 
+    def check_numerics(self):
+        """Reads the library's two device-side counters (synchronises): class ids outside [0, n_class) -- the reference's
+        nn.Embedding would have raised -- and forward operands beyond fp16's range, which the fp16 operand planes clamp.
+        On the latter the library is switched to bf16 planes (fp32's exponent range, 16-bit operand precision) for every
+        later step, loudly."""
+        bad = _C.index_errors()
+        if bad:
+            raise IndexError(f"{bad} class ids outside [0, {self.n_class}) reached the embedding / projection kernels")
+        sat = _C.saturation_count()
+        if sat:
+            import warnings
+            _C.set_option("fwd_bf16", 1)
+            warnings.warn(f"dvdgan_b200: {sat} groups of forward activations / weights exceeded fp16's range (65504) and "
+                          "were clamped in the tensor-core operand planes; switching to bf16 operand planes "
+                          "(dvd_set_option('fwd_bf16', 1)) from here on", RuntimeWarning)
+        return sat
+
     # ------------------------------------------------------------------ loop (trainer.py:189-343)
     def epoch2step(self):
         self.epoch = 0
@@ -357,6 +374,8 @@ class Trainer(object):
                         self.writer.add_scalar("data/" + k, float(out[k]), step)
                     self.writer.add_text("logs", log_str, step)
                 print(log_str)
+            if step % self.log_step == 0 or step == self.total_step:
+                self.check_numerics()
             if step % self.sample_step == 0 and self.rank == 0:
                 self.sample(step)
             if step % self.model_save_step == 0 and self.rank == 0:

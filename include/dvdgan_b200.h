@@ -44,12 +44,19 @@ int dvd_prof_dump(const char* path);
  * validated configuration; nothing is read from the environment inside the library.
  *   "simt_only" 0   fp32 FFMA conv engine for every convolution (the tests' cross-check of the tensor-core engine)
  *   "pair" 1, "persist" 1, "occ2" 1, "epi_prefetch" 1     tile / scheduling variants of the tcgen05 engine
- *   "oneacc" 0      persistent tiles use ONE fp32 accumulator for all three bf16 products and double-buffer it
+ *   "oneacc" 0      persistent tiles use ONE fp32 accumulator for all three products and double-buffer it (implies
+ *                   "fwd_bf16": measured +2 % on the step, Generator output 1.2e-3 from the fp32 reference)
+ *   "fwd_bf16" 0    bf16 operand planes in the forward too: fp32's exponent range at 16-bit operand precision; the
+ *                   default fp16 planes (22 bits) clamp |x| > 65504 and count it (dvd_saturation_count)
  *   "gru_fused" 1, "gru_share_planes" 1, "gru_bwd_planes" 1   ConvGRU fusion levels
  *   "flash_attn" 1  attention on the tensor cores without the N x N map (0: materialised SIMT path)
  * Unknown names are an error. */
 int dvd_set_option(const char* name, int value);
 int dvd_get_option(const char* name, int* value);
+/* Forward operands of the tensor-core engine are fp16 (hi, lo) planes; |x| > 65504 is clamped and counted.  Reads -- and
+ * with reset != 0 clears -- the count of clamped 8-element groups on the current device (0 in a healthy run; the fp32
+ * reference would carry such values on).  Synchronises `stream`.  Remedy: dvd_set_option("fwd_bf16", 1). */
+int dvd_saturation_count(unsigned int* count, int reset, void* stream);
 /* High-water mark / currently reserved bytes of the current device's default stream-ordered memory pool: the bf16
  * operand planes of the tensor-core engine are cudaMallocAsync'ed there (freed in stream order after each call). */
 int dvd_scratch_bytes(long long* high_water, long long* reserved);
@@ -76,7 +83,9 @@ typedef struct {
   int out_act;                /* 0 none, 1 relu, 2 tanh (applied after bias / residual) */
   int res_up;                 /* residual is read at (h>>res_up, w>>res_up) */
   int64_t r_s1, r_s2, r_cs;   /* residual strides (if res != NULL) */
-  int x_kind;                 /* reserved (ABI 1 used it to pick fp16 operand planes; all planes are bf16 now) */
+  int x_kind;                 /* tensor-core path: 1 = x holds forward activations / the conv is a forward conv: fp16
+                                 operand planes (22 bits, |x| <= 65504, see dvd_saturation_count); 0 = x may hold
+                                 gradients: bf16 planes (fp32's exponent range) */
 } dvd_conv_desc;
 
 int dvd_conv_fwd(const dvd_conv_desc* d, const float* x, const float* w_packed, const float* bias,
@@ -175,6 +184,21 @@ int dvd_attn_bwd(const float* q, int64_t q_bs, const float* k, int64_t k_bs, con
                  const float* attn, float* dattn, const float* dout, int64_t do_bs, float* dq_, int64_t dq_bs, float* dk_,
                  int64_t dk_bs, float* dv_, int64_t dv_bs, int batch, int dq, int dv, int Nq, int Nk,
                  int q_token_major, void* stream);
+
+/* The same contraction on the tensor cores (tcgen05, bf16-split operands, fp32 TMEM accumulators) WITHOUT the N x N map:
+ * a two-pass softmax (log-sum-exp per query first, then exp(s - lse) straight into the P.V product), the backward
+ * recomputes P from lse.  Covers channel-major q/k/v with dq <= 64, dv <= 256 (backward: 128), token counts that are
+ * multiples of 8 (dvd_attn_flash_supported); the caller falls back to dvd_attn_fwd / dvd_attn_bwd otherwise.
+ * `workspace`: dvd_attn_flash_workspace_bytes bytes of device memory (operand planes), free to reuse after the call. */
+int dvd_attn_flash_supported(int batch, int dq, int dv, int Nq, int Nk, int backward);
+size_t dvd_attn_flash_workspace_bytes(int batch, int dq, int dv, int Nq, int Nk, int backward);
+int dvd_attn_flash_fwd(const float* q, int64_t q_bs, const float* k, int64_t k_bs, const float* v, int64_t v_bs,
+                       float* out, int64_t o_bs, float* lse, int batch, int dq, int dv, int Nq, int Nk,
+                       void* workspace, size_t ws_bytes, void* stream);
+int dvd_attn_flash_bwd(const float* q, int64_t q_bs, const float* k, int64_t k_bs, const float* v, int64_t v_bs,
+                       const float* out, int64_t o_bs, const float* dout, int64_t do_bs, const float* lse,
+                       float* dq_, int64_t dq_bs, float* dk_, int64_t dk_bs, float* dv_, int64_t dv_bs, int batch,
+                       int dq, int dv, int Nq, int Nk, void* workspace, size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Pooling, resampling, helpers

@@ -15,7 +15,7 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.used --for
 nproc > $O/nproc.txt
 has() { [[ " $STAGES " == *" $1 "* ]]; }
 if has tests; then
-  timeout ${TEST_TIMEOUT:-1500} python -m pytest tests -m gpu -x -q --durations=15 > $O/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a $O/pytest_gpu.log
+  timeout ${TEST_TIMEOUT:-1500} python -m pytest tests -m gpu ${PYTEST_ARGS:--x} -q --durations=15 > $O/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a $O/pytest_gpu.log
   tail -30 $O/pytest_gpu.log
 fi
 if has bench; then

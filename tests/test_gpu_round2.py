@@ -234,22 +234,68 @@ def test_second_backward_through_gru_raises(dev):
         s.backward()
 
 
-@pytest.mark.parametrize("scale", [1e5, 3e8, 1e-7, 1e-20])
-def test_conv_engine_keeps_fp32_range(dev, scale):
-    """The tensor-core engine splits fp32 operands into bf16 (hi, lo) planes, which have fp32's exponent range:
-    activations of magnitude 1e5 (above fp16's 65504) or 3e8, and gradients of 1e-7 / 1e-20, must come out as accurate
-    as O(1) inputs do (ABI 1 clamped forward operands to +-65504)."""
-    from dvdgan_b200 import ops
+@pytest.mark.parametrize("scale", [1e5, 3e8])
+def test_forward_range_guard(dev, scale):
+    """Forward operands ride fp16 (hi, lo) planes: 22 significant bits, which the 1e-3 contract needs over 48 recurrent
+    frames, but |x| <= 65504.  Activations of 1e5 / 3e8 are clamped there -- and COUNTED (never silently): the counter
+    is what Trainer.check_numerics turns into a switch to bf16 planes, under which the same conv is exact again."""
+    from dvdgan_b200 import _C, ops
     torch.manual_seed(3)
     N, Ci, Co, H = 8, 128, 128, 32
     x = torch.randn(N, Ci, H, H, device=dev) * scale
     w = torch.randn(Co, Ci, 3, 3, device=dev) * 0.05
     ref = torch.nn.functional.conv2d(x.double(), w.double(), padding=1)
-    y = ops.conv_raw(x, ops.pack_weight(w), None, Co, (1, 3, 3), x_kind=1)
-    assert rel(y, ref) < 2e-5, rel(y, ref)
+    wp = ops.pack_weight(w)
+    _C.saturation_count()
+    y = ops.conv_raw(x, wp, None, Co, (1, 3, 3), x_kind=1)
+    assert _C.saturation_count() > 0 and rel(y, ref) > 1e-2            # clamped, and flagged
+    y1 = ops.conv_raw(torch.randn(N, Ci, H, H, device=dev) * 100.0, wp, None, Co, (1, 3, 3), x_kind=1)
+    assert _C.saturation_count() == 0 and torch.isfinite(y1).all()      # ordinary magnitudes: nothing counted
+    _C.set_option("fwd_bf16", 1)
+    try:
+        y = ops.conv_raw(x, wp, None, Co, (1, 3, 3), x_kind=1)
+    finally:
+        _C.set_option("fwd_bf16", 0)
+    assert _C.saturation_count() == 0 and rel(y, ref) < 2e-5, rel(y, ref)
+
+
+@pytest.mark.parametrize("scale", [1e5, 1e-7, 1e-20])
+def test_gradient_operands_keep_fp32_range(dev, scale):
+    """Everything that holds gradients (dgrad / wgrad operands) is split into bf16 planes, which have fp32's exponent
+    range: 1e-7 / 1e-20 gradients (below fp16's 6e-8 subnormal floor) and 1e5 ones come out as accurate as O(1) do."""
+    from dvdgan_b200 import ops
+    torch.manual_seed(3)
+    N, Ci, Co, H = 8, 128, 128, 32
+    x = torch.randn(N, Ci, H, H, device=dev)
     dy = torch.randn(N, Co, H, H, device=dev) * scale
-    dwp = ops.wgrad_raw(torch.randn(N, Ci, H, H, device=dev), dy, (1, 3, 3))
-    assert torch.isfinite(dwp).all() and float(dwp.abs().max()) > 0
+    w = torch.randn(Co, Ci, 3, 3, device=dev) * 0.05
+    gref = torch.nn.grad.conv2d_weight(x.double().cpu(), w.shape, dy.double().cpu(), padding=1)
+    g = ops.unpack_wgrad(ops.wgrad_raw(x, dy, (1, 3, 3)), w)
+    assert rel(g, gref) < 2e-5, rel(g, gref)
+    dref = torch.nn.grad.conv2d_input(x.shape, w.double().cpu(), dy.double().cpu(), padding=1)
+    dx = ops.conv_raw(dy, ops.pack_weight(w, transpose=True), None, Ci, (1, 3, 3))       # x_kind = 0: gradient operand
+    assert rel(dx, dref) < 2e-5, rel(dx, dref)
+
+
+def test_trainer_switches_planes_when_activations_saturate(dev, golden):
+    from dvdgan_b200 import _C
+    from dvdgan_b200.trainer import Trainer
+    fx = golden("step.pt")
+    torch.cuda.set_device(dev)
+    # ch = 8: wide enough (64 channels and up) for the convolutions to run on the tensor-core engine
+    tr = Trainer(None, argparse.Namespace(**dict(fx["cfg"], g_chn=8, ds_chn=8, dt_chn=8)))
+    _C.saturation_count()
+    try:
+        with torch.no_grad():            # blow the first ConvGRU's input up past fp16's range
+            tr.G.affine_transfrom.weight.mul_(1e7)
+        tr.train_step(fx["clips"][0], fx["labels"][0])
+        with pytest.warns(RuntimeWarning, match="bf16 operand planes"):
+            assert tr.check_numerics() > 0
+        assert _C.get_option("fwd_bf16") == 1
+        tr.train_step(fx["clips"][1], fx["labels"][1])
+        assert tr.check_numerics() == 0
+    finally:
+        _C.set_option("fwd_bf16", 0)
 
 
 @pytest.mark.parametrize("case", [
