@@ -5,6 +5,7 @@ import torch
 import torch.nn as nn
 
 from .. import ops
+from .Attention import SelfAttention, SeparableAttn
 from .ConvGRU import ConvGRU
 from .GResBlock import GResBlock
 from .Normalization import SpectralNorm
@@ -12,7 +13,11 @@ from .Normalization import SpectralNorm
 
 class Generator(nn.Module):
 
-    def __init__(self, in_dim=120, latent_dim=4, n_class=4, ch=32, n_frames=48, hierar_flag=False):
+    def __init__(self, in_dim=120, latent_dim=4, n_class=4, ch=32, n_frames=48, hierar_flag=False, attention=False):
+        """``attention=True`` (not a reference argument, default off) wires in the two non-local blocks the reference
+        imports but leaves commented out (Generator.py:28-36): the pooled 3-D ``SelfAttention(8*ch)`` after the first
+        ConvGRU stage and ``SeparableAttn(4*ch)`` in front of the last GResBlock.  Their parameters are extra
+        state_dict keys (``self_attn.*``, ``sep_attn.*``); with the default the key set is the reference's."""
         super().__init__()
         self.in_dim = in_dim
         self.latent_dim = latent_dim
@@ -45,6 +50,17 @@ class Generator(nn.Module):
             res(4 * ch, 2 * ch),
         ])
         self.colorize = SpectralNorm(nn.Conv2d(2 * ch, 3, kernel_size=(3, 3), padding=1))
+        self.attention = bool(attention)
+        if self.attention:
+            self.self_attn = SelfAttention(8 * ch)
+            self.sep_attn = SeparableAttn(4 * ch)
+
+    def _attend(self, attn, y, B, T):
+        """y (B*T, C, W, H) with b-major rows -> the 3-D block over (B, C, T, W, H) -> back."""
+        _, C, W, H = y.shape
+        v = ops.Permute5Fn.apply(y.view(B, T, C, W, H), (0, 2, 1, 3, 4))
+        v = attn(v)
+        return ops.Permute5Fn.apply(v, (0, 2, 1, 3, 4)).view(B * T, C, W, H)
 
     def forward(self, x, class_id, taps=None):
         """x: z (B,in_dim) float32; class_id (B,) int64 -> (B, n_frames, 3, 16*latent_dim, 16*latent_dim)."""
@@ -64,7 +80,11 @@ class Generator(nn.Module):
                     y = conv.forward_sequence(y.view(B, T, C, W, H))
                 _, _, C, W, H = y.shape
                 y = y.view(B * T, C, W, H)                              # b-major rows: b*T + t
+                if self.attention and k == 0:
+                    y = self._attend(self.self_attn, y, B, T)
             else:
+                if self.attention and k == len(self.conv) - 1:
+                    y = self._attend(self.sep_attn, y, B, T)
                 # the reference conditions row i on sample i % B (condition.repeat(T,1), Q1)
                 y = conv(y, cond)
             if taps is not None:

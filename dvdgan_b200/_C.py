@@ -47,6 +47,8 @@ _SIGS = {
     "dvd_specnorm_fwd": (I, [P, I, I, P, P, P, P, P]),
     "dvd_specnorm_bwd": (I, [P, P, P, P, P, I, I, P, I, P, P]),
     "dvd_bn_stats": (I, [P, I, I, I, I, F, F, P, P, P, P, P, P, P]),
+    "dvd_bn_stats_ex": (I, [P, I, I, I, I, F, F, P, P, P, P, P, P, I, I, P]),
+    "dvd_cbn_bwd_ex": (I, [P, P, I, P, P, P, I, I, I, I, I, I, I, P, P, P, I, P]),
     "dvd_cbn_apply": (I, [P, P, I, P, P, I, I, I, I, I, I, P, P]),
     "dvd_cbn_bwd": (I, [P, P, I, P, P, P, I, I, I, I, I, I, I, P, P, P, P]),
     "dvd_attn_fwd": (I, [P, L, P, L, P, L, P, P, L, I, I, I, I, I, I, P]),

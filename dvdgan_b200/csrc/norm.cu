@@ -530,15 +530,19 @@ extern "C" int dvd_specnorm_bwd(const float* g, const float* w_bar, const float*
   return 0;
 }
 
-extern "C" int dvd_bn_stats(const float* x, int N, int C, int HW, int training, float momentum, float eps,
-                            float* running_mean, float* running_var, int64_t* num_batches_tracked, float* mean,
-                            float* rstd, void* scratch, void* stream) {
+// phase 0: everything.  Cross-replica statistics (Generator.py:57-58's TODO) split the call around a collective:
+// phase 1 leaves the per-channel (sum, sum of squares) of this rank's N*HW elements in `scratch` (2C doubles), the caller
+// sums that over the ranks, phase 2 finalises with `count_scale` x (N*HW) elements.
+extern "C" int dvd_bn_stats_ex(const float* x, int N, int C, int HW, int training, float momentum, float eps,
+                               float* running_mean, float* running_var, int64_t* num_batches_tracked, float* mean,
+                               float* rstd, void* scratch, int phase, int count_scale, void* stream) {
   dvd::ProfScope _ps(3, "bn_stats", dvd::as_stream(stream));
-  DVD_CHECK_ARG(x && mean && rstd && scratch && N > 0 && C > 0 && HW > 0);
+  DVD_CHECK_ARG(x && mean && rstd && scratch && N > 0 && C > 0 && HW > 0 && phase >= 0 && phase <= 2 && count_scale >= 1);
   DVD_CHECK_ARG(training || (running_mean && running_var));
+  DVD_CHECK_ARG(phase == 0 || training);
   cudaStream_t st = as_stream(stream);
   double* acc = reinterpret_cast<double*>(scratch);
-  if (training) {
+  if (training && phase != 2) {
     DVD_CUDA(cudaMemsetAsync(acc, 0, sizeof(double) * 2 * C, st));
     // enough blocks to cover the machine: C x splits over the batch
     int splits = ceil_div(4 * num_sms(), C);
@@ -552,11 +556,18 @@ extern "C" int dvd_bn_stats(const float* x, int N, int C, int HW, int training, 
       bn_partial_kernel<<<dim3(C, splits), 256, 0, st>>>(x, N, C, HW, npb, acc);
     DVD_LAUNCH_CHECK();
   }
-  bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, st>>>(acc, C, (double)N * HW, training, momentum, eps, running_mean,
-                                                       running_var, reinterpret_cast<long long*>(num_batches_tracked),
-                                                       mean, rstd);
+  if (phase == 1) return 0;
+  bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, st>>>(acc, C, (double)N * HW * count_scale, training, momentum, eps,
+                                                       running_mean, running_var,
+                                                       reinterpret_cast<long long*>(num_batches_tracked), mean, rstd);
   DVD_LAUNCH_CHECK();
   return 0;
+}
+extern "C" int dvd_bn_stats(const float* x, int N, int C, int HW, int training, float momentum, float eps,
+                            float* running_mean, float* running_var, int64_t* num_batches_tracked, float* mean,
+                            float* rstd, void* scratch, void* stream) {
+  return dvd_bn_stats_ex(x, N, C, HW, training, momentum, eps, running_mean, running_var, num_batches_tracked, mean, rstd,
+                         scratch, 0, 1, stream);
 }
 
 extern "C" int dvd_cbn_apply(const float* x, const float* gb, int gb_rows, const float* mean, const float* rstd, int N,
@@ -578,18 +589,22 @@ extern "C" int dvd_cbn_apply(const float* x, const float* gb, int gb_rows, const
   return 0;
 }
 
-extern "C" int dvd_cbn_bwd(const float* x, const float* gb, int gb_rows, const float* mean, const float* rstd,
-                           const float* dy, int N, int C, int H, int W, int relu, int up, int training, float* dx,
-                           float* dgb, float* scratch, void* stream) {
+// phase 0: everything.  Cross-replica statistics: phase 1 computes dgb and leaves this rank's per-channel
+// (mean(dxhat), mean(dxhat * xhat)) in `scratch` (2C floats), the caller AVERAGES that over the (equal-sized) ranks,
+// phase 2 computes dx from the averaged means.
+extern "C" int dvd_cbn_bwd_ex(const float* x, const float* gb, int gb_rows, const float* mean, const float* rstd,
+                              const float* dy, int N, int C, int H, int W, int relu, int up, int training, float* dx,
+                              float* dgb, float* scratch, int phase, void* stream) {
   dvd::ProfScope _ps(3, "cbn_bwd", dvd::as_stream(stream));
   DVD_CHECK_ARG(x && gb && mean && rstd && dy && dx && dgb && scratch && N > 0 && C > 0 && (up == 0 || up == 1));
-  DVD_CHECK_ARG(gb_rows > 0 && gb_rows <= N);
+  DVD_CHECK_ARG(gb_rows > 0 && gb_rows <= N && phase >= 0 && phase <= 2 && (phase == 0 || training));
   cudaStream_t st = as_stream(stream);
-  if (gb_rows != N) DVD_CUDA(cudaMemsetAsync(dgb, 0, sizeof(float) * (size_t)gb_rows * 2 * C, st));
   const int64_t planes = (int64_t)N * C;
   const bool vec = vec_ok(x, dy, dx, H, W, up);
   const int lpp = lanes_per_plane(up ? (H * W) >> 1 : (H * W) >> 2);
   const int nb = walker_blocks(planes, lpp);
+  if (phase != 2) {
+  if (gb_rows != N) DVD_CUDA(cudaMemsetAsync(dgb, 0, sizeof(float) * (size_t)gb_rows * 2 * C, st));
   if (vec) {
     if (up) cbn_bwd_plane_vec_kernel<true><<<nb, 256, 0, st>>>(x, gb, gb_rows, mean, rstd, dy, planes, N, C, H, W, relu, lpp, dgb);
     else cbn_bwd_plane_vec_kernel<false><<<nb, 256, 0, st>>>(x, gb, gb_rows, mean, rstd, dy, planes, N, C, H, W, relu, lpp, dgb);
@@ -602,6 +617,8 @@ extern "C" int dvd_cbn_bwd(const float* x, const float* gb, int gb_rows, const f
     cbn_bwd_chan_kernel<<<C, 256, 0, st>>>(gb, dgb, gb_rows, C, 1.f / ((float)N * H * W), scratch);
     DVD_LAUNCH_CHECK();
   }
+  }
+  if (phase == 1) return 0;
   if (vec) {
     if (up) cbn_bwd_dx_vec_kernel<true><<<nb, 256, 0, st>>>(x, gb, gb_rows, mean, rstd, dy, scratch, planes, C, H, W, relu, training, lpp, dx);
     else cbn_bwd_dx_vec_kernel<false><<<nb, 256, 0, st>>>(x, gb, gb_rows, mean, rstd, dy, scratch, planes, C, H, W, relu, training, lpp, dx);
@@ -611,4 +628,9 @@ extern "C" int dvd_cbn_bwd(const float* x, const float* gb, int gb_rows, const f
   }
   DVD_LAUNCH_CHECK();
   return 0;
+}
+extern "C" int dvd_cbn_bwd(const float* x, const float* gb, int gb_rows, const float* mean, const float* rstd,
+                           const float* dy, int N, int C, int H, int W, int relu, int up, int training, float* dx,
+                           float* dgb, float* scratch, void* stream) {
+  return dvd_cbn_bwd_ex(x, gb, gb_rows, mean, rstd, dy, N, C, H, W, relu, up, training, dx, dgb, scratch, 0, stream);
 }

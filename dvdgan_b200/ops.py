@@ -295,10 +295,41 @@ class SNWeightFn(torch.autograd.Function):
         return sn_backward(_c(g), w, u, v, sigma), None, None
 
 
+# Cross-replica BatchNorm statistics (opt-in; the reference leaves it as a TODO, Generator.py:57-58): with a process
+# group set here, the per-channel sums of every ConditionalNorm are reduced over the ranks in the forward (sum, sum of
+# squares) and in the backward (the two means of the batch-norm gradient), so that N data-parallel ranks normalise
+# exactly like one process holding the global batch.  None = per-replica statistics, the reference's DataParallel.
+SYNC_BN_GROUP = None
+
+
+def set_sync_bn(group):
+    """group: a torch.distributed process group (or True for the default group), None to switch it off."""
+    global SYNC_BN_GROUP
+    SYNC_BN_GROUP = group
+
+
+def _sync_world():
+    import torch.distributed as dist
+    if SYNC_BN_GROUP is None or not (dist.is_available() and dist.is_initialized()):
+        return None, 1
+    g = None if SYNC_BN_GROUP is True else SYNC_BN_GROUP
+    n = dist.get_world_size(g)
+    return g, n
+
+
 def _cbn_stats(x, running_mean, running_var, nbt, training, momentum, eps):
     N, C, H, W = x.shape
     mean, rstd = _new((C,), x), _new((C,), x)
     scratch = torch.empty(2 * C, device=x.device, dtype=torch.float64)
+    group, world = _sync_world()
+    if training and world > 1:
+        import torch.distributed as dist
+        args = (ptr(x), N, C, H * W, 1, momentum, eps, ptr(running_mean), ptr(running_var), ptr(nbt), ptr(mean),
+                ptr(rstd), ptr(scratch))
+        call("dvd_bn_stats_ex", *args, 1, 1)
+        dist.all_reduce(scratch, op=dist.ReduceOp.SUM, group=group)
+        call("dvd_bn_stats_ex", *args, 2, world)
+        return mean, rstd
     call("dvd_bn_stats", ptr(x), N, C, H * W, int(training), momentum, eps, ptr(running_mean), ptr(running_var),
          ptr(nbt), ptr(mean), ptr(rstd), ptr(scratch))
     return mean, rstd
@@ -317,6 +348,16 @@ def _cbn_backward(x, gb, mean, rstd, dy, relu, up, training):
     dx = _new(x.shape, x)
     dgb = _new(gb.shape, gb)
     scratch = _new((2 * C,), x)
+    group, world = _sync_world()
+    if training and world > 1:
+        import torch.distributed as dist
+        args = (ptr(x), ptr(gb), gb.shape[0], ptr(mean), ptr(rstd), ptr(dy), N, C, H, W, int(relu), up, 1, ptr(dx),
+                ptr(dgb), ptr(scratch))
+        call("dvd_cbn_bwd_ex", *args, 1)
+        dist.all_reduce(scratch, op=dist.ReduceOp.SUM, group=group)
+        call("dvd_axpby", ptr(scratch), 0.0, 1.0 / world, 2 * C, ptr(scratch))        # equal shards: mean of the means
+        call("dvd_cbn_bwd_ex", *args, 2)
+        return dx, dgb
     call("dvd_cbn_bwd", ptr(x), ptr(gb), gb.shape[0], ptr(mean), ptr(rstd), ptr(dy), N, C, H, W, int(relu), up,
          int(training), ptr(dx), ptr(dgb), ptr(scratch))
     return dx, dgb

@@ -164,7 +164,10 @@ class Trainer(object):
     """Same constructor contract as the reference: ``Trainer(data_loader, config)``; ``config`` carries the
     reference's argparse fields (parameter.py:6-79).  Not reference flags, all optional: ``latent_dim`` (128x128 /
     256x256 clips), ``gru_lean`` ('auto' | True | False: ConvGRU BPTT keeps h only and recomputes the gates),
-    ``shard_optimizer`` (reduce-scatter / sharded Adam / all-gather), ``sample_path``."""
+    ``shard_optimizer`` (reduce-scatter / sharded Adam / all-gather), ``sample_path``, ``g_attention`` (the reference's
+    commented-out non-local blocks in G), ``sync_bn`` (cross-replica statistics in G's conditional batch norms, the
+    reference's TODO), ``dp_shard=(world, rank)`` (act as shard ``rank`` of a ``world``-way data-parallel job WITHOUT a
+    process group: same global RNG draws and slicing, no collectives -- for debugging one rank in isolation)."""
 
     def __init__(self, data_loader, config):
         self.data_loader = data_loader
@@ -196,8 +199,11 @@ class Trainer(object):
         self.world_size = dist.get_world_size() if self.distributed else 1
         self.rank = dist.get_rank() if self.distributed else 0
         self.device = torch.device("cuda", torch.cuda.current_device())
-        self.shard = shard_batch(self.batch_size, self.world_size, self.rank)      # raises if not divisible
-        self.local_batch = self.batch_size // self.world_size
+        shard_world, shard_rank = getattr(c, "dp_shard", None) or (self.world_size, self.rank)
+        self.shard = shard_batch(self.batch_size, shard_world, shard_rank)      # raises if not divisible
+        self.local_batch = self.batch_size // shard_world
+        self.g_attention = bool(getattr(c, "g_attention", False))
+        ops.set_sync_bn(True if (getattr(c, "sync_bn", False) and self.distributed) else None)
         lean = getattr(c, "gru_lean", "auto")
         if lean == "auto":      # full BPTT state (20 B per hidden element) only while it stays under ~1/3 of the device
             full = ops.gru_state_bytes(self.local_batch, self.n_frames, self.g_chn, self.latent_dim, lean=False)
@@ -214,7 +220,7 @@ class Trainer(object):
     # ------------------------------------------------------------------ model / optimizers
     def build_model(self):
         self.G = Generator(self.z_dim, latent_dim=self.latent_dim, n_class=self.n_class, ch=self.g_chn,
-                           n_frames=self.n_frames).to(self.device)
+                           n_frames=self.n_frames, attention=self.g_attention).to(self.device)
         self.D_s = SpatialDiscriminator(chn=self.ds_chn, n_class=self.n_class).to(self.device)
         self.D_t = TemporalDiscriminator(chn=self.dt_chn, n_class=self.n_class).to(self.device)
         if self.distributed:            # replicas start identical (DataParallel re-broadcasts every forward)
@@ -258,7 +264,7 @@ class Trainer(object):
     def _local(self, real_videos, real_labels):
         """Accept the loader's global batch (sliced to this rank's shard) or an already-local shard; enforce the
         dtypes the kernels assume (the reference's modules would raise or cast on anything else)."""
-        if real_videos.shape[0] == self.batch_size and self.world_size > 1:
+        if real_videos.shape[0] == self.batch_size and self.local_batch != self.batch_size:
             real_videos, real_labels = real_videos[self.shard], real_labels[self.shard]
         if real_videos.shape[0] != self.local_batch:
             raise ValueError(f"expected {self.local_batch} clips per rank (global batch {self.batch_size} over "

@@ -159,6 +159,13 @@ int dvd_specnorm_bwd(const float* g, const float* w_bar, const float* u, const f
 int dvd_bn_stats(const float* x, int N, int C, int HW, int training, float momentum, float eps,
                  float* running_mean, float* running_var, int64_t* num_batches_tracked, float* mean, float* rstd,
                  void* scratch, void* stream);
+/* The same in phases, for statistics over the replicas of a data-parallel job (the reference's TODO at
+ * Generator.py:57-58): phase 0 = everything (dvd_bn_stats); phase 1 leaves this rank's per-channel (sum, sum of squares)
+ * in `scratch` (2*C doubles) for the caller to sum over the ranks; phase 2 finalises mean / rstd / running statistics
+ * from the summed scratch, counting count_scale * N * HW elements (count_scale = number of equal-sized ranks). */
+int dvd_bn_stats_ex(const float* x, int N, int C, int HW, int training, float momentum, float eps,
+                    float* running_mean, float* running_var, int64_t* num_batches_tracked, float* mean, float* rstd,
+                    void* scratch, int phase, int count_scale, void* stream);
 /* y = relu?(gb[r][c] * xhat + gb[r][C+c]) nearest-upsampled by 2^up (Normalization.py:82-86 +
  * GResBlock.py:52-55): the conditional affine, activation and F.interpolate in one pass.
  * gb has gb_rows rows and row r = n % gb_rows (gb_rows == N: one row per image; gb_rows == B reproduces
@@ -170,6 +177,12 @@ int dvd_cbn_apply(const float* x, const float* gb, int gb_rows, const float* mea
 int dvd_cbn_bwd(const float* x, const float* gb, int gb_rows, const float* mean, const float* rstd, const float* dy,
                 int N, int C, int H, int W, int relu, int up, int training, float* dx, float* dgb, float* scratch,
                 void* stream);
+/* In phases (cross-replica statistics): phase 1 computes dgb and leaves this rank's per-channel (mean(dxhat),
+ * mean(dxhat * xhat)) in `scratch` (2*C floats) for the caller to AVERAGE over the equal-sized ranks; phase 2 computes dx
+ * from the averaged scratch; phase 0 = everything (dvd_cbn_bwd). */
+int dvd_cbn_bwd_ex(const float* x, const float* gb, int gb_rows, const float* mean, const float* rstd, const float* dy,
+                   int N, int C, int H, int W, int relu, int up, int training, float* dx, float* dgb, float* scratch,
+                   int phase, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Attention core (Discriminators.py:108-114, Attention.py:92-101,165-176):

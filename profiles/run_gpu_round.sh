@@ -4,7 +4,10 @@
 #   bench    the default bench line (config 2) with the per-shape event profile
 #   configs  bench lines of BASELINE.json configs 3, 4, 5 at their per-GPU batch on ONE GPU
 #   oneacc   A/B of the double-buffered single-accumulator tiles: micro-benchmark, Generator error by stage, bench line
-#   ncu      `ncu --set full` of the dominant kernels + the launch list of a --frames 8 step
+#   ncu      `ncu --set full` of the dominant kernels (GEMMs, operand split, CBN / BN statistics, attention) + the launch
+#            list of a --frames 8 step
+#   refgpu   informational: the unmodified reference under eager PyTorch / cuDNN on this GPU (profiles/ref_eager_b200.py)
+#   sanitize compute-sanitizer memcheck + racecheck over smoke() and a small attention case
 # Outputs land in gpurun_out/<tag>/ (scratch); summaries are copied into profiles/ afterwards.
 #   usage: gpurun --timeout 2400 -- bash profiles/run_gpu_round.sh [tag]
 TAG=${1:-r2}
@@ -37,9 +40,27 @@ if has oneacc; then
   DVD_OPTIONS=oneacc=1 timeout 400 python bench.py --no-cpu-baseline --prof-dump $O/prof_oneacc.tsv > $O/bench_oneacc.json 2> $O/bench_oneacc.err
   echo "bench oneacc rc=$?"; cat $O/bench_oneacc.json
 fi
+if has refgpu; then
+  timeout 900 python profiles/ref_eager_b200.py --batch ${REF_BATCH:-32} > $O/ref_eager_b200.jsonl 2> $O/ref_eager_b200.err
+  echo "ref eager rc=$?"; cat $O/ref_eager_b200.jsonl; tail -3 $O/ref_eager_b200.err
+fi
+if has sanitize; then
+  for tool in memcheck racecheck; do
+    timeout 900 compute-sanitizer --tool $tool --print-limit 30 python -c "import __graft_entry__ as g; g.smoke()" \
+        > $O/sanitizer_${tool}_smoke.log 2>&1; echo "$tool smoke rc=$?"; tail -4 $O/sanitizer_${tool}_smoke.log
+    timeout 900 compute-sanitizer --tool $tool --print-limit 30 python -m pytest tests/test_gpu_round2.py -q -x \
+        -k "flash_attention_matches and (shape4 or shape2)" > $O/sanitizer_${tool}_attn.log 2>&1; echo "$tool attn rc=$?"
+    tail -4 $O/sanitizer_${tool}_attn.log
+  done
+fi
 if has ncu; then
   timeout 400 ncu --set full --clock-control none --import-source on -k regex:conv_tma_ -c 4 -f -o $O/conv_tma_s9 \
       python profiles/conv_microbench.py --reps 1 --only s9_cell1_h_ur > $O/ncu_full.log 2>&1; echo "ncu full rc=$?"
+  # memory-bound kernels and attention: two launches of each family from a short step (B = 64, 4 frames)
+  timeout 600 ncu --set full --clock-control none --import-source on \
+      -k regex:"prep_planes|cbn_apply_vec|bn_partial_vec|cbn_bwd_dx_vec|attn_tc_kernel|gru_bwd1_planes" -s 40 -c 24 -f \
+      -o $O/membound python bench.py --frames 4 --steps 1 --warmup 0 --no-e2e --no-cpu-baseline \
+      > $O/ncu_membound.log 2>&1; echo "ncu membound rc=$?"
   timeout 300 python bench.py --frames 8 --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --prof-dump $O/prof_f8.tsv \
       > $O/bench_f8.json 2> $O/bench_f8.err; echo "bench f8 rc=$?"
   timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $O/launches_f8.csv \

@@ -43,7 +43,33 @@ CASES = {
 }
 
 
+def _sampled_rel(a, b):
+    """global rel-L2 between two dicts of samples (name -> dict(v=...))"""
+    num = sum(float((a[k]["v"].double() - b[k]["v"].double()).norm() ** 2) for k in b)
+    den = sum(float(b[k]["v"].double().norm() ** 2) for k in b)
+    return (num / max(den, 1e-300)) ** 0.5
+
+
 def make_case(name, c):
+    """The fixture proper comes from a run on all cores; a second run of the same reference code on HALF the cores
+    (a different summation order inside MKL-DNN, nothing else) measures the reference's own run-to-run noise on the
+    sampled gradients (SURVEY 7 #2), which the GPU tests use as their yardstick."""
+    n = os.cpu_count() or 1
+    torch.set_num_threads(n)
+    fx = run_case(name, c)
+    torch.set_num_threads(max(1, n // 2))
+    fx2 = run_case(name + " (half the threads)", c)
+    torch.set_num_threads(n)
+    fx["noise"] = dict(threads=(n, max(1, n // 2)),
+                       G_out=float((fx["G"]["out"]["v"] - fx2["G"]["out"]["v"]).norm() / fx["G"]["out"]["v"].norm()),
+                       G_grads=_sampled_rel(fx2["G"]["grads"], fx["G"]["grads"]),
+                       Ds_grads=_sampled_rel(fx2["Ds"]["grads"], fx["Ds"]["grads"]),
+                       Dt_grads=_sampled_rel(fx2["Dt"]["grads"], fx["Dt"]["grads"]))
+    print(name, "reference noise:", fx["noise"], flush=True)
+    save(f"full_{name}.pt", fx)
+
+
+def run_case(name, c):
     from Module.Generator import Generator
     from Module.Discriminators import SpatialDiscriminator, TemporalDiscriminator
     t0 = time.time()
@@ -91,11 +117,28 @@ def make_case(name, c):
     fx["Dt"] = dict(out=o.detach().clone(), dx=sample("dt.dx", xt.grad, 1 << 16),
                     grads={k: sample("gt." + k, p.grad, 1024) for k, p in Dt.named_parameters() if p.grad is not None})
     print(f"{name}: done {time.time() - t0:.0f}s", flush=True)
-    save(f"full_{name}.pt", fx)
+    return fx
 
 
 def make_step_full():
-    """Two steps of the reference Trainer at config-2 width (ch = 32, 48 frames, 64x64, 101 classes, k = 8), 1 clip."""
+    """Two steps of the reference Trainer at config-2 width (ch = 32, 48 frames, 64x64, 101 classes, k = 8), 1 clip;
+    run twice (all cores / half the cores) so that the fixture also holds the reference's own noise on the parameter
+    updates (beta1 = 0: the first Adam step is lr * sign(g), so every near-zero gradient whose sign flips under
+    summation-order noise moves its parameter by 2 * lr)."""
+    n = os.cpu_count() or 1
+    torch.set_num_threads(n)
+    fx = run_step_full()
+    torch.set_num_threads(max(1, n // 2))
+    fx2 = run_step_full()
+    torch.set_num_threads(n)
+    fx["noise"] = dict(threads=(n, max(1, n // 2)),
+                       losses=[abs(a - b) for a, b in zip(fx["losses"], fx2["losses"])],
+                       delta={k: _sampled_rel(fx2["delta"][k], fx["delta"][k]) for k in fx["delta"]})
+    print("c2step reference noise:", fx["noise"], flush=True)
+    save("full_c2step.pt", fx)
+
+
+def run_step_full():
     torch.nn.Module.cuda = lambda self, *a, **k: self
     torch.Tensor.cuda = lambda self, *a, **k: self
     import trainer as ref_trainer
@@ -132,13 +175,12 @@ def make_step_full():
         torch.Tensor.backward = bw
     delta = {k: {n: sample(f"d.{k}.{n}", p.detach() - pre[k][n], 1024)
                  for n, p in net.named_parameters() if p.requires_grad} for k, net in nets.items()}
-    save("full_c2step.pt", dict(cfg=vars(cfg), seed=seed, rng_seed=77, n_steps=n_steps, gamma_s=0.3, gamma_t=-0.4,
-                                fp=fp, losses=losses, delta=delta))
+    return dict(cfg=vars(cfg), seed=seed, rng_seed=77, n_steps=n_steps, gamma_s=0.3, gamma_t=-0.4, fp=fp,
+                losses=losses, delta=delta)
 
 
 if __name__ == "__main__":
     _install_shims()
-    torch.set_num_threads(os.cpu_count() or 1)
     todo = sys.argv[1:] or ["c5", "c4", "c3", "c2step"]
     for t in todo:
         if t == "c2step":

@@ -1,0 +1,115 @@
+"""Two-GPU data-parallel tests (NCCL, one process per GPU; skipped on a one-GPU box): the reference's DataParallel
+semantics -- global batch drawn from ONE RNG stream and sharded, per-replica BatchNorm statistics, gradients summed --
+plus the opt-in sharded optimizer and cross-replica BatchNorm."""
+import argparse
+import os
+import sys
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pytestmark = pytest.mark.gpu
+
+CFG = dict(adv_loss="hinge", z_dim=120, g_chn=8, ds_chn=8, dt_chn=8, n_frames=4, k_sample=2, n_class=3, batch_size=4,
+           d_iters=1, g_lr=5e-5, d_lr=5e-5, beta1=0.0, beta2=0.9, lr_schr="const", latent_dim=4, gru_lean=False)
+
+
+def _data():
+    g = torch.Generator().manual_seed(99)
+    return torch.rand(4, 3, 4, 64, 64, generator=g) * 2 - 1, torch.randint(0, 3, (4,), generator=g)
+
+
+def _flat_state(net):
+    """every Parameter (weights and the spectral norms' u / v), not the BatchNorm buffers, which are per replica"""
+    return torch.cat([p.detach().reshape(-1).float() for p in net.parameters()])
+
+
+def _worker(rank, world, port, extra, q):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    from dvdgan_b200.trainer import Trainer
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    torch.manual_seed(5 + rank)           # different seeds on purpose: the Trainer must unify init and RNG stream
+    tr = Trainer(None, argparse.Namespace(**dict(CFG, **extra)))
+    clips, labels = _data()
+    out = tr.train_step(clips, labels)    # the global batch: each rank keeps its shard
+    out2 = tr.train_step(clips, labels)
+    torch.cuda.synchronize()
+    q.put((rank, dict(losses=[float(out[k]) for k in ("ds_loss", "dt_loss", "g_loss")],
+                      losses2=[float(out2[k]) for k in ("ds_loss", "dt_loss", "g_loss")],
+                      G=_flat_state(tr.G).cpu(), Ds=_flat_state(tr.D_s).cpu(),
+                      bn_mean=tr.G.conv[1].CBNorm1.bn.running_mean.cpu().clone())))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _run(extra):
+    world = 2
+    port = 29600 + os.getpid() % 2000
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, extra, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=600) for _ in range(world))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    return res
+
+
+@pytest.fixture(scope="module")
+def two_gpus():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+
+
+def test_ddp_first_step_equals_mean_of_isolated_shards(two_gpus):
+    """A 2-rank job vs its two shards computed in isolation on one GPU (dp_shard): each rank's D losses are its shard's
+    (same broadcast weights, same global RNG draws, its slice of the batch), replicas stay bit-identical, BatchNorm
+    statistics stay per replica (the reference's DataParallel semantics)."""
+    sys.path.insert(0, ROOT)
+    from dvdgan_b200.trainer import Trainer
+    res = _run({})
+    assert torch.equal(res[0]["G"], res[1]["G"]) and torch.equal(res[0]["Ds"], res[1]["Ds"])        # replicas identical
+    assert not torch.equal(res[0]["bn_mean"], res[1]["bn_mean"])        # BatchNorm statistics stay per replica
+    torch.cuda.set_device(0)
+    clips, labels = _data()
+    shard_losses = []
+    for r in range(2):
+        torch.manual_seed(5)              # rank 0's seed: its init and RNG stream are what the job broadcast
+        tr = Trainer(None, argparse.Namespace(**dict(CFG, dp_shard=(2, r))))
+        out = tr.train_step(clips, labels)
+        shard_losses.append([float(out[k]) for k in ("ds_loss", "dt_loss", "g_loss")])
+    # a rank's D losses are its own shard's (same weights, same draws); g_loss follows the averaged D updates, so it only
+    # agrees approximately (lr = 5e-5)
+    for r in range(2):
+        assert res[r]["losses"][:2] == pytest.approx(shard_losses[r][:2], rel=1e-5, abs=1e-6)
+        assert res[r]["losses"][2] == pytest.approx(shard_losses[r][2], rel=1e-2, abs=1e-3)
+    assert res[0]["losses"] != res[1]["losses"]                          # different shards of the batch
+
+
+def test_ddp_sharded_optimizer_matches_replicated(two_gpus):
+    """reduce-scatter -> Adam on 1/N of the arena -> all-gather gives the parameters all-reduce + full Adam gives."""
+    a = _run({})
+    b = _run({"shard_optimizer": True})
+    assert torch.equal(b[0]["G"], b[1]["G"])
+    for key in ("G", "Ds"):
+        # same gradients up to the reduction order of the collective; Adam (beta1 = 0) turns a gradient sign flip of a
+        # near-zero element into a 2*lr difference, so compare with an absolute bound of a few lr
+        assert float((a[0][key] - b[0][key]).abs().max()) < 5e-4, key
+    assert a[0]["losses2"] == pytest.approx(b[0]["losses2"], rel=1e-3, abs=1e-4)
+
+
+def test_ddp_cross_replica_batchnorm(two_gpus):
+    """sync_bn: every ConditionalNorm of G normalises with the statistics of the global batch, so the running
+    statistics agree across the ranks (they differ per replica otherwise) and training stays finite and in sync."""
+    res = _run({"sync_bn": True})
+    assert torch.equal(res[0]["G"], res[1]["G"])
+    assert torch.allclose(res[0]["bn_mean"], res[1]["bn_mean"], rtol=0, atol=0)
+    assert all(torch.isfinite(torch.tensor(res[r]["losses2"])).all() for r in range(2))

