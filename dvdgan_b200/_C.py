@@ -79,6 +79,8 @@ _SIGS = {
     "dvd_index_errors": (I, [ctypes.POINTER(ctypes.c_uint), I, P]),
     "dvd_dhead_fwd": (I, [P, I, I, I, I, I, P, P, P, P, P, P, P, P, P]),
     "dvd_dhead_bwd": (I, [P, P, P, I, I, I, I, I, P, P, P, P, P, P, P, P, P, P]),
+    "dvd_clip_transform": (I, [P, I, I, I, I, P, P, P, P, I, P, P, I, I, I, F, ctypes.POINTER(c_float),
+                               ctypes.POINTER(c_float), P, P]),
     "dvd_gan_loss_fwd": (I, [P, I, F, I, I, P, P]),
     "dvd_gan_loss_bwd": (I, [P, P, I, F, I, P, P]),
     "dvd_adam_step": (I, [P, P, P, P, L, F, F, F, F, I, F, P]),

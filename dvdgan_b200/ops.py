@@ -473,7 +473,7 @@ class GRULayerFn(torch.autograd.Function):
             h0 = _c(h0)
         cfg = (B, T, Cx, Ch, H, W, k, x_bs, x_ts, T_bcast)
         gates, h, rh = GRULayerFn._run_fwd(x, h0, wu, wr, wo, bu, br, bo, cfg)
-        ctx.lean = bool(GRU_LEAN) and torch.is_grad_enabled()
+        ctx.lean = bool(GRU_LEAN)       # (grad mode is always off inside Function.forward: do not test it here)
         if ctx.lean:
             ctx.save_for_backward(x, h0, wu, wr, wo, bu, br, bo, h)        # gates / rh are dropped here
         else:

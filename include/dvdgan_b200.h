@@ -273,6 +273,18 @@ int dvd_dhead_bwd(const float* x, const float* feat, const float* dout, int N, i
                   const float* w_lin, const float* sigma_l, const float* emb, const float* sigma_e,
                   const int64_t* class_id, float* dx, float* dwl, float* db, float* demb, void* stream);
 
+/* Input pipeline on the GPU (Dataloader/datasets/ucf101.py:177-199 with the transforms of main.py:33-56):
+ * frames uint8 [B][T][Hs][Ws][3] (decoded RGB) -> per-clip crop `box` = (x0, y0, w, h), already rounded the way
+ * PIL.Image.crop rounds -> bilinear resize to OH x OW exactly as Pillow's ImagingResample does for 8-bit images (two
+ * passes, 22-bit fixed-point coefficients, uint8 intermediate) -> horizontal flip where flip[b] != 0 ->
+ * (pixel / norm_value - mean[c]) / std[c] in fp32 -> out (B, 3, T, OH, OW).
+ * xb / yb: [B][OW|OH][2] = (first source index inside the crop, tap count); xk / yk: [B][OW|OH][xks|yks] fixed-point
+ * coefficients; both come from the host restatement of Pillow's precompute_coeffs (dvdgan_b200/data.py).  mean3 / std3
+ * are HOST pointers to three floats. */
+int dvd_clip_transform(const uint8_t* frames, int B, int T, int Hs, int Ws, const int* box, const int* flip,
+                       const int* xb, const int* xk, int xks, const int* yb, const int* yk, int yks, int OH, int OW,
+                       float norm_value, const float* mean3, const float* std3, float* out, void* stream);
+
 /* Losses (trainer.py:114-121): sign = -1 for real_flag; hinge: mean(relu(1 + sign*x)); wgan: mean(sign*x).
  * loss[0] (+)= value;  bwd: dx = gout[0] * dloss/dx. */
 int dvd_gan_loss_fwd(const float* x, int n, float sign, int hinge, int accumulate, float* loss, void* stream);

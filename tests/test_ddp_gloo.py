@@ -33,7 +33,7 @@ def _cpu_adam(p, g, m, v, lr, b1, b2, eps, t, scale):
     p.addcdiv_(m, (v.sqrt() / bc2 ** 0.5).add_(eps), value=-lr / bc1)
 
 
-def _worker(rank, world, port, q, shard=False):
+def _worker(rank, world, port, q, shard=False, overlap=False):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -45,6 +45,9 @@ def _worker(rank, world, port, q, shard=False):
     net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 1))
     opt = FlatAdam(net, 1e-2, (0.0, 0.9), shard=(world, rank) if shard else None)
     assert all(p.data_ptr() >= opt.flat_p.data_ptr() for p in net.parameters())   # params are arena views
+    if overlap:     # one all-reduce per top-level child, started by a hook as soon as the child's gradients exist
+        opt.enable_overlap(net)
+        assert opt._buckets == [(0, 2), (2, 4)]
     if shard:       # 41 parameters over 2 ranks: arena padded to 42, moments exist for this rank's 21 only
         assert opt.flat_p.numel() == 42 and opt.m.numel() == 21 and opt.v.numel() == 21
     x = torch.randn(8, 6)
@@ -54,19 +57,22 @@ def _worker(rank, world, port, q, shard=False):
         opt.zero_grad()
         loss = ((net(x[sl]) - y[sl]) ** 2).mean()
         loss.backward()
+        if overlap:
+            assert len(opt._pending) == 2          # both buckets were launched during the backward pass
         opt.step(world)
     q.put((rank, opt.flat_p[:opt.numel].clone()))
     dist.barrier()
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("shard", [False, True], ids=["allreduce", "reduce_scatter_sharded_adam_all_gather"])
-def test_flat_adam_allreduce_matches_global_batch(shard):
+@pytest.mark.parametrize("shard,overlap", [(False, False), (True, False), (False, True)],
+                         ids=["allreduce", "reduce_scatter_sharded_adam_all_gather", "bucketed_allreduce_during_backward"])
+def test_flat_adam_allreduce_matches_global_batch(shard, overlap):
     world = 2
-    port = 29500 + (os.getpid() + 7 * shard) % 2000
+    port = 29500 + (os.getpid() + 7 * shard + 13 * overlap) % 2000
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q, shard)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, shard, overlap)) for r in range(world)]
     for p in procs:
         p.start()
     res = dict(q.get(timeout=120) for _ in range(world))
