@@ -99,6 +99,7 @@ def parse():
                     help="ConvGRU BPTT keeps h only and recomputes the gates (auto: when the full state would not fit)")
     ap.add_argument("--shard-optimizer", action="store_true", help="reduce-scatter -> sharded Adam -> all-gather")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--force-port", action="store_true", help="reference arm: time the oracle port even if baseline/_ref exists")
     ap.add_argument("--cpu-frames", type=int, default=None, help="debug: shrink the CPU sample")
     ap.add_argument("--prof-dump", default=None, help="write the per-shape launch table of the timed steps here")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only (ncu launch list): skip the e2e leg")
@@ -159,19 +160,91 @@ def cpu_step_time(a, steps, warmup, frames=None):
     return B / dt, cores, sample, dt
 
 
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")          # git-ignored copy of /root/reference; travels with the snapshot
+
+
+def ref_cpu_step_time(a, steps, warmup, frames=None):
+    """Time the UNMODIFIED reference's own Trainer.train() (trainer.py:189-343) on the host cores: baseline/_ref on
+    sys.path, the three shims of SURVEY 8c (tensorboardX stub, .cuda() no-ops, a synthetic loader), B = 2 clips per step
+    (the per-clip CPU cost is flat in B).  Only for 64x64 clips: the reference trainer cannot build a
+    Generator with another latent_dim (trainer.py:349)."""
+    import types
+    import torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    tbx = types.ModuleType("tensorboardX")
+    tbx.SummaryWriter = type("SummaryWriter", (), {"__init__": lambda self, *aa, **kk: None})
+    sys.modules["tensorboardX"] = tbx
+    sys.path.insert(0, REF_DIR)
+    torch.nn.Module.cuda = lambda self, *aa, **kk: self
+    torch.Tensor.cuda = lambda self, *aa, **kk: self
+    import trainer as ref_trainer
+    T, B = frames or a.frames, 2
+    n = steps + warmup
+    torch.manual_seed(0)
+    clips = [torch.rand(B, 3, T, 64, 64) * 2 - 1 for _ in range(n)]
+    labels = [torch.randint(0, a.classes, (B,)) for _ in range(n)]
+
+    class Loader:
+        def __len__(self):
+            return n
+
+        def __iter__(self):
+            return iter(zip(clips, labels))
+    cfg = argparse.Namespace(
+        model="dvd-gan", adv_loss="hinge", imsize=64, g_num=5, z_dim=120, g_chn=a.ch, ds_chn=a.ch, dt_chn=a.ch,
+        n_frames=T, g_conv_dim=64, d_conv_dim=64, lr_schr="const", lambda_gp=10, total_epoch=1, d_iters=1, g_iters=1,
+        batch_size=B, num_workers=0, g_lr=5e-5, d_lr=5e-5, lr_decay=0.9999, beta1=0.0, beta2=0.9,
+        pretrained_model=None, n_class=a.classes, k_sample=min(a.k_sample, T), dataset="synthetic",
+        use_tensorboard=False, test_batch_size=1, image_path="", log_path="/tmp/dvd_ref/log",
+        model_save_path="/tmp/dvd_ref/m", sample_path="/tmp/dvd_ref/s", log_epoch=10 ** 6, sample_epoch=10 ** 6,
+        model_save_epoch=10 ** 6, version="bench", gpus="", parallel=False)
+    real_stdout = os.dup(1)          # the reference prints banners: keep stdout for the one JSON line
+    os.dup2(2, 1)
+    try:
+        tr = ref_trainer.Trainer(Loader(), cfg)
+        marks = []
+        bw = torch.Tensor.backward
+
+        def backward(self, *aa, **kk):          # the third backward of a step (g_loss) closes it
+            r = bw(self, *aa, **kk)
+            marks.append(time.perf_counter())
+            return r
+        torch.Tensor.backward = backward
+        t_start = time.perf_counter()
+        try:
+            tr.train()
+        finally:
+            torch.Tensor.backward = bw
+    finally:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
+    ends = [t_start] + marks[2::3]          # step boundaries (the optimizer step of G falls into the next interval)
+    dt = (ends[-1] - ends[warmup]) / steps
+    sample = f"{steps} full G+Ds+Dt step(s) of the unmodified reference Trainer.train() (baseline/_ref), {B} clips x {T}f x " \
+             f"64x64, k={min(a.k_sample, T)}, {a.classes} classes, ch={a.ch}, fp32, {warmup} warm-up"
+    return B / dt, cores, sample, dt
+
+
 def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     # warm-ups are full steps too (~10-25 s each on 8-16 cores); cap them so the run ends within minutes
-    v, cores, sample, dt = cpu_step_time(a, a.steps, min(a.warmup, 1), a.cpu_frames)
+    kind = "reference" if (os.path.isdir(REF_DIR) and a.latent_dim == 4 and not a.force_port) else "port"
+    if kind == "reference":
+        v, cores, sample, dt = ref_cpu_step_time(a, a.steps, min(a.warmup, 1), a.cpu_frames)
+    else:
+        v, cores, sample, dt = cpu_step_time(a, a.steps, min(a.warmup, 1), a.cpu_frames)
     line = {
         "impl": "reference", "metric": metric_name(a), "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(a, a.batch, max(a.gpus, 1)) + "; CPU sample = 1 clip per step",
+        "config": {"workload": workload_name(a, a.batch, max(a.gpus, 1)) + "; CPU sample = "
+                               + ("2 clips" if kind == "reference" else "1 clip") + " per step",
                    "timing": "host wall clock"},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -369,8 +442,19 @@ def run_b200(a):
             "last_losses": losses[-1] if losses else None,
         }
         if world == 1 and not a.no_cpu_baseline:
-            v, cores, sample, _ = cpu_step_time(a, 1, 0, a.cpu_frames)
-            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+            # the reference arm, bounded to one step, in its own process (it patches .cuda() and puts baseline/_ref on
+            # sys.path): the unmodified reference when baseline/_ref is there, the oracle port otherwise
+            cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                   "--config", str(a.config), "--frames", str(a.frames), "--classes", str(a.classes),
+                   "--k-sample", str(a.k_sample), "--ch", str(a.ch), "--latent-dim", str(a.latent_dim)]
+            if a.cpu_frames:
+                cmd += ["--cpu-frames", str(a.cpu_frames)]
+            r = subprocess.run(cmd, capture_output=True, text=True, env={k: v for k, v in os.environ.items()
+                                                                       if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")})
+            try:
+                line["cpu_baseline"] = json.loads(r.stdout.strip().splitlines()[-1])["cpu_baseline"]
+            except Exception:
+                line["cpu_baseline"] = {"error": (r.stderr or r.stdout)[-300:]}
         sys.stdout.flush()
         os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:

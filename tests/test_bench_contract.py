@@ -18,9 +18,31 @@ def test_reference_arm_prints_one_json_line():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["unit"] == "clips/s" and d["higher_is_better"] is True
     assert d["value"] > 0 and d["ms_per_step"] > 0
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    # "reference" when the git-ignored copy baseline/_ref is present (the unmodified reference's own Trainer), else the port
+    assert d["cpu_baseline"]["kind"] in ("port", "reference") and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"] == {"value": d["value"], "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["gpu_launches"] == 0 and d["vs_baseline"] is None
+
+
+def test_reference_arm_port_fallback():
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                        "--warmup", "0", "--cpu-frames", "4", "--force-port"], capture_output=True, text=True,
+                       timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    assert d["cpu_baseline"]["kind"] == "port" and d["value"] > 0
+
+
+def test_workload_names_follow_the_arguments():
+    sys.path.insert(0, ROOT)
+    import argparse
+    import bench
+    a = argparse.Namespace(frames=48, latent_dim=8, classes=101, ch=32, k_sample=8)
+    assert bench.metric_name(a) == "clips/sec (48f x 128x128) G+Ds+Dt step"
+    assert "configs[2]" in bench.workload_name(a, 32, 8) and "32/GPU x 8 GPU" in bench.workload_name(a, 32, 8)
+    assert bench.step_work(a) == (32.76, 15.40)
+    a.frames = 20
+    assert "custom shape" in bench.workload_name(a, 4, 1) and bench.step_work(a) == (None, None)
 
 
 def test_reference_arm_other_ranks_stay_silent():
