@@ -175,6 +175,7 @@ struct AttnP {
   int rows, cols;          // tokens on the CTA side / streamed side
   int nz;                  // width of OUT (multiple of 16, <= 256)
   int k2;                  // 64-wide K blocks of the second stage-1 GEMM (NS = 2)
+  int kq;                  // UMMA_K = 16 steps of the S GEMM that hold data: ceil(dq / 16) (the planes are zero beyond dq)
   int out_z;               // valid columns of OUT
   int ld;                  // queries per batch item (stride of L / D)
   const float* L;
@@ -266,8 +267,7 @@ __global__ void __launch_bounds__(192, 1) attn_tc_kernel(const __grid_constant__
 #pragma unroll
           for (int i = 0; i < 6; ++i) {
             const uint64_t da = make_desc(s_x1 + pa[i] * XB), db = make_desc(s_y1 + pb[i] * YB);
-#pragma unroll
-            for (int kk = 0; kk < KP / 16; ++kk)
+            for (int kk = 0; kk < ap.kq; ++kk)
               mma_f16(tmem_base + COL_S, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), id_s, (i | kk) != 0);
           }
         }
@@ -525,6 +525,7 @@ static int split_cm(const float* src, int64_t bs, int B, int C, int N, int RP, c
 struct Pass {
   int B, rows, cols;
   const Planes* x1; const Planes* y1;             // 3 planes, [B][rows|cols][64]
+  int dq = KP;                                    // channels of x1 / y1 that hold data
   const Planes* x2 = nullptr; const Planes* y2 = nullptr; int k2 = 0;      // 2 planes, [B][rows|cols][64*k2]
   const Planes* z = nullptr; int nz = 0;          // 2 planes, [B][nz][cols]
   const float* L = nullptr; const float* D = nullptr; int ld = 0;
@@ -550,6 +551,7 @@ static int launch(const Pass& ps, cudaStream_t st) {
   AttnP ap;
   memset(&ap, 0, sizeof(ap));
   ap.rows = ps.rows; ap.cols = ps.cols; ap.nz = LSE ? 16 : ps.nz; ap.k2 = ps.k2; ap.out_z = ps.out_z; ap.ld = ps.ld;
+  ap.kq = ceil_div(ps.dq, 16);
   ap.L = ps.L; ap.D = ps.D; ap.Lout = ps.Lout; ap.out = ps.out; ap.out_bs = ps.out_bs; ap.out_zs = ps.out_zs;
   uint32_t off = 3 * BR * 128;
   ap.off_x2 = off; off += NS == 2 ? 2 * ps.k2 * BR * 128 : 0;
@@ -605,7 +607,7 @@ extern "C" int dvd_attn_flash_fwd(const float* q, int64_t q_bs, const float* k, 
   DVD_TRY(attn::split_tm(k, k_bs, batch, dq, Nk, attn::KP, 3, ws.k_tm, st));
   DVD_TRY(attn::split_cm(v, v_bs, batch, dv, Nk, zv, ws.v_cm, st));
   attn::Pass ps;
-  ps.B = batch; ps.rows = Nq; ps.cols = Nk; ps.x1 = &ws.q_tm; ps.y1 = &ws.k_tm; ps.Lout = lse;
+  ps.B = batch; ps.rows = Nq; ps.cols = Nk; ps.x1 = &ws.q_tm; ps.y1 = &ws.k_tm; ps.Lout = lse; ps.dq = dq;
   DVD_TRY((attn::launch<1, false, true>(ps, st)));
   ps.Lout = nullptr; ps.L = lse; ps.ld = Nq; ps.z = &ws.v_cm; ps.nz = zv; ps.out = out; ps.out_bs = o_bs; ps.out_zs = Nq;
   ps.out_z = dv;
@@ -642,7 +644,7 @@ extern "C" int dvd_attn_flash_bwd(const float* q, int64_t q_bs, const float* k, 
   // dV = P^T dO: rows = keys, columns = queries
   {
     attn::Pass ps;
-    ps.B = batch; ps.rows = Nk; ps.cols = Nq; ps.x1 = &ws.k_tm; ps.y1 = &ws.q_tm; ps.L = lse; ps.ld = Nq;
+    ps.B = batch; ps.rows = Nk; ps.cols = Nq; ps.x1 = &ws.k_tm; ps.y1 = &ws.q_tm; ps.L = lse; ps.ld = Nq; ps.dq = dq;
     ps.z = &ws.do_cm; ps.nz = zv; ps.out = dv_; ps.out_bs = dv_bs; ps.out_zs = Nk; ps.out_z = dv;
     DVD_TRY((attn::launch<1, true, false>(ps, st)));
   }
@@ -650,7 +652,7 @@ extern "C" int dvd_attn_flash_bwd(const float* q, int64_t q_bs, const float* k, 
   {
     attn::Pass ps;
     ps.B = batch; ps.rows = Nq; ps.cols = Nk; ps.x1 = &ws.q_tm; ps.y1 = &ws.k_tm; ps.x2 = &ws.do_tm; ps.y2 = &ws.v_tm;
-    ps.k2 = dvP / 64; ps.L = lse; ps.D = ws.D; ps.ld = Nq;
+    ps.k2 = dvP / 64; ps.L = lse; ps.D = ws.D; ps.ld = Nq; ps.dq = dq;
     ps.z = &ws.k_cm; ps.nz = zq; ps.out = dq_; ps.out_bs = dq_bs; ps.out_zs = Nq; ps.out_z = dq;
     DVD_TRY((attn::launch<2, false, false>(ps, st)));
   }
@@ -658,7 +660,7 @@ extern "C" int dvd_attn_flash_bwd(const float* q, int64_t q_bs, const float* k, 
   {
     attn::Pass ps;
     ps.B = batch; ps.rows = Nk; ps.cols = Nq; ps.x1 = &ws.k_tm; ps.y1 = &ws.q_tm; ps.x2 = &ws.v_tm; ps.y2 = &ws.do_tm;
-    ps.k2 = dvP / 64; ps.L = lse; ps.D = ws.D; ps.ld = Nq;
+    ps.k2 = dvP / 64; ps.L = lse; ps.D = ws.D; ps.ld = Nq; ps.dq = dq;
     ps.z = &ws.q_cm; ps.nz = zq; ps.out = dk_; ps.out_bs = dk_bs; ps.out_zs = Nk; ps.out_z = dq;
     DVD_TRY((attn::launch<2, true, false>(ps, st)));
   }

@@ -38,6 +38,14 @@ struct TmaOperands {
 //  mode 2 (h-half of out, Cout = Ch):            y = o = tanh(v); out2 = hprev * (1 - u) + o * u  (+ planes of it)
 // hprev / ugate / out2 are (B, Ch, H, W) views with batch strides hp_s1 / u_s1 / o2_s1 and channel stride H*W;
 // the planes are dense [B*H*W][pl_Cp] in the forward plane format, the A operand of the next h-half GEMM.
+// BPTT epilogues of the two per-step dgrad GEMMs; v = accumulator, gates hold (u | r | o) activated:
+//  mode 3 (d(rh) = conv_o^T(da_o), Cout = Ch):  carry += v * r;  da_r = v * hprev * r * (1 - r)  -> reset slot of the
+//         frame's gates (fp32) and channels [Ch, 2Ch) of its bf16 gradient planes.   gate = ugate, carry = out2.
+//  mode 4 (conv_ur^T(da_u | da_r), Cout = Ch):  dhn = dh_prev + carry_in + v  is the whole gradient of h_{t-1}; the
+//         elementwise part of step t-1 follows at once:  da_o = dhn * u * (1 - o^2),  da_u = dhn * (o - h2) * u * (1 - u)
+//         -> update / out slots of frame t-1's gates and channels [0, Ch) / [2Ch, 3Ch) of its planes;
+//         carry_next = dhn * (1 - u).   gate(t-1) = ugate, h2 = hprev (h_{t-2}, may be null), carry_next = out2.
+// planes: frame image b at pl + b * pl_img + pix * pl_Cp (channels-last, pl_Cp = round64(3Ch)).
 struct GruEpi {
   int mode = 0;
   int Ch = 0;
@@ -50,6 +58,11 @@ struct GruEpi {
   void* pl_hi = nullptr;
   void* pl_lo = nullptr;
   int pl_Cp = 0;
+  // modes 3 / 4 only
+  int64_t pl_img = 0;
+  const float* carry_in = nullptr;     // mode 4: carry after mode 3 of the same step (batch stride o2_s1)
+  const float* dh_prev = nullptr;      // mode 4: external gradient of h_{t-1}
+  int64_t dh_s1 = 0;
 };
 bool tma_fwd_launch_ex_eligible(const ConvP& p);
 int tma_fwd_launch_ex(ConvP& p, const TmaOperands* ops, const GruEpi* epi, cudaStream_t st);

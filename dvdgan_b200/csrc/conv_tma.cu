@@ -613,7 +613,69 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
                          reinterpret_cast<__nv_bfloat16*>(ge.pl_lo) + (int64_t)m * ge.pl_Cp + c0, o2, fp.fp16);
       }
     };
+    // BPTT epilogues (modes 3 / 4, see GruEpi), eight channels at a time to bound the live registers
+    auto emit_bptt32 = [&](int cb, const float* v) {
+      const int co0 = n0 + cb;
+      if (co0 >= d.Cout) return;
+      const int nb = m / p.DHW;
+      const int pix = m - nb * p.DHW;
+      float* gate = const_cast<float*>(ge.ugate) + (int64_t)nb * ge.u_s1 + pix;        // + channel * DHW
+      __nv_bfloat16* ph = reinterpret_cast<__nv_bfloat16*>(ge.pl_hi) + (int64_t)nb * ge.pl_img + (int64_t)pix * ge.pl_Cp;
+      __nv_bfloat16* pl = reinterpret_cast<__nv_bfloat16*>(ge.pl_lo) + (int64_t)nb * ge.pl_img + (int64_t)pix * ge.pl_Cp;
+      float* cw = ge.out2 + (int64_t)nb * ge.o2_s1 + pix;
+#pragma unroll
+      for (int s8 = 0; s8 < 4; ++s8) {
+        const int c0 = co0 + 8 * s8;
+        if (ge.mode == 3) {
+          float r[8], h[8], cr[8], dar[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            r[j] = __ldcg(gate + (int64_t)(ge.Ch + c0 + j) * p.DHW);
+            h[j] = __ldg(ge.hprev + (int64_t)nb * ge.hp_s1 + (int64_t)(c0 + j) * p.DHW + pix);
+            cr[j] = __ldcg(cw + (int64_t)(c0 + j) * p.DHW);
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float drh = v[8 * s8 + j];
+            cw[(int64_t)(c0 + j) * p.DHW] = fmaf(drh, r[j], cr[j]);
+            dar[j] = drh * h[j] * r[j] * (1.f - r[j]);
+            gate[(int64_t)(ge.Ch + c0 + j) * p.DHW] = dar[j];
+          }
+          uint4 hi, lo;
+          bf16_split8(dar, &hi, &lo);
+          *reinterpret_cast<uint4*>(ph + ge.Ch + c0) = hi;
+          *reinterpret_cast<uint4*>(pl + ge.Ch + c0) = lo;
+        } else {
+          float u[8], o[8], h2[8], dhn[8], dau[8], dao[8];
+          const float* cin = ge.carry_in + (int64_t)nb * ge.o2_s1 + pix;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            u[j] = __ldcg(gate + (int64_t)(c0 + j) * p.DHW);
+            o[j] = __ldcg(gate + (int64_t)(2 * ge.Ch + c0 + j) * p.DHW);
+            h2[j] = ge.hprev ? __ldg(ge.hprev + (int64_t)nb * ge.hp_s1 + (int64_t)(c0 + j) * p.DHW + pix) : 0.f;
+            dhn[j] = __ldg(ge.dh_prev + (int64_t)nb * ge.dh_s1 + (int64_t)(c0 + j) * p.DHW + pix) +
+                     __ldcg(cin + (int64_t)(c0 + j) * p.DHW) + v[8 * s8 + j];
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            dao[j] = dhn[j] * u[j] * (1.f - o[j] * o[j]);
+            dau[j] = dhn[j] * (o[j] - h2[j]) * u[j] * (1.f - u[j]);
+            gate[(int64_t)(c0 + j) * p.DHW] = dau[j];
+            gate[(int64_t)(2 * ge.Ch + c0 + j) * p.DHW] = dao[j];
+            cw[(int64_t)(c0 + j) * p.DHW] = dhn[j] * (1.f - u[j]);
+          }
+          uint4 hi, lo;
+          bf16_split8(dau, &hi, &lo);
+          *reinterpret_cast<uint4*>(ph + c0) = hi;
+          *reinterpret_cast<uint4*>(pl + c0) = lo;
+          bf16_split8(dao, &hi, &lo);
+          *reinterpret_cast<uint4*>(ph + 2 * ge.Ch + c0) = hi;
+          *reinterpret_cast<uint4*>(pl + 2 * ge.Ch + c0) = lo;
+        }
+      }
+    };
     auto emit32 = [&](int cb, const float* v) {
+      if (ge.mode >= 3) { emit_bptt32(cb, v); return; }
       if (ge.mode) { emit_gru32(cb, v); return; }
       const int co0 = n0 + cb;
       if (co0 >= d.Cout) return;
@@ -652,7 +714,25 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
     // While the main loop runs these warps are idle: pull everything the epilogue will read into L2, so its loads pay
     // an L2 hit instead of a DRAM round trip per 32-channel chunk.
     if (fp.prefetch && !p.atomic_out && (d.accumulate || ge.mode)) mbar_wait(smem_u32(bars.late(buf)), tpar);
-    if (fp.prefetch && ok && !p.atomic_out && (d.accumulate || ge.mode)) {
+    if (fp.prefetch && ok && ge.mode >= 3) {
+      const int nb = m / p.DHW, pix = m - nb * p.DHW;
+      const int cend = min(BN, d.Cout - n0);
+      const float* gate = ge.ugate + (int64_t)nb * ge.u_s1 + pix;
+      for (int j = 0; j < cend; ++j) {
+        if (EW == 8 && ((j >> 5) & 1) != half) continue;
+        const int c = n0 + j;
+        if (ge.hprev) prefetch_l2(ge.hprev + (int64_t)nb * ge.hp_s1 + (int64_t)c * p.DHW + pix);
+        if (ge.mode == 3) {
+          prefetch_l2(gate + (int64_t)(ge.Ch + c) * p.DHW);
+          prefetch_l2(ge.out2 + (int64_t)nb * ge.o2_s1 + (int64_t)c * p.DHW + pix);
+        } else {
+          prefetch_l2(gate + (int64_t)c * p.DHW);
+          prefetch_l2(gate + (int64_t)(2 * ge.Ch + c) * p.DHW);
+          prefetch_l2(ge.dh_prev + (int64_t)nb * ge.dh_s1 + (int64_t)c * p.DHW + pix);
+          prefetch_l2(ge.carry_in + (int64_t)nb * ge.o2_s1 + (int64_t)c * p.DHW + pix);
+        }
+      }
+    } else if (fp.prefetch && ok && !p.atomic_out && (d.accumulate || ge.mode)) {
       const int nb = m / p.DHW, pix = m - nb * p.DHW;
       const int cend = min(BN, d.Cout - n0);
       for (int j = 0; j < cend; ++j) {
@@ -1115,7 +1195,9 @@ int tma_fwd_launch_ex(ConvP& p, const TmaOperands* ops, const GruEpi* epi, cudaS
   fp.CoutP = CoutP;
   if (epi) fp.gru = *epi;
   fp.prefetch = get_option(OPT_EPI_PREFETCH);
-  if (fp.gru.mode) DVD_CHECK_ARG(d.accumulate && fp.gru.Ch % 32 == 0 && !d.out_act && !p.res && !p.bias);
+  if (fp.gru.mode) DVD_CHECK_ARG(fp.gru.Ch % 32 == 0 && !d.out_act && !p.res && !p.bias);
+  if (fp.gru.mode == 1 || fp.gru.mode == 2) DVD_CHECK_ARG(d.accumulate);
+  if (fp.gru.mode >= 3) DVD_CHECK_ARG(!d.accumulate && d.Cout == fp.gru.Ch && fp.gru.pl_hi && fp.gru.pl_lo && fp.gru.out2);
   fp.fp16 = (d.x_kind == 1 && tma_forward_planes_fp16()) ? 1 : 0;
   fp.lo_inv = fp.fp16 ? 1.f / kLoScaleFp16 : 1.f;
   const int64_t ctas = (int64_t)mt * ceil_div(d.Cout, bn);

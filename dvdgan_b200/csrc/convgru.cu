@@ -437,58 +437,97 @@ extern "C" int dvd_convgru_layer_bwd(const float* x, int64_t x_bs, int64_t x_ts,
     pl_hi = reinterpret_cast<__nv_bfloat16*>(gp.p);
     pl_lo = pl_hi + elems;
   }
+  // Fused BPTT: the gate-gradient math between the two dgrad GEMMs of a step, and between one step and the next, runs
+  // in their epilogues (GruEpi modes 3 / 4): two launches per step instead of four.  Only where the GEMMs fill the
+  // machine without split-K (the small early stages keep the separate kernels and their split-K dgrads).
+  const bool bptt_fused = gplanes && get_option(OPT_GRU_BWD_FUSED) &&
+                          (int64_t)ceil_div(B * HW, 128) * ceil_div(Ch, 128) >= num_sms();
+  bool need_k1 = true;        // the elementwise part 1 of this step has not been done by the previous step's epilogue
   for (int t = T - 1; t >= 0; --t) {
     const float* hp = t > 0 ? h + (int64_t)(t - 1) * h_ts : h0;
     const int64_t hp_bs = t > 0 ? h_bs : chw;
     float* g_t = gates + (int64_t)t * g_ts;
+    float* carry_next = (carry_out == ws.carry0) ? ws.carry1 : ws.carry0;
     const dim3 pgrid(ceil_div(HW, 32), Ch / 64, B);
-    if (gplanes) {
-      ProfScope ps(3, "gru_bwd1", st);
-      gru_bwd1_planes_kernel<<<pgrid, 256, 0, st>>>(g_t, g_bs, hp, hp_bs, dh + (int64_t)t * h_ts, h_bs, carry_in,
-                                                     carry_out, Ch, HW, pl_hi + t * pl_frame, pl_lo + t * pl_frame,
-                                                     pl_img, G3P);
-    } else {
-      ProfScope ps(3, "gru_bwd1", st);
-      gru_bwd1_kernel<<<eb, 256, 0, st>>>(g_t, g_bs, hp, hp_bs, dh + (int64_t)t * h_ts, h_bs, carry_in, carry_out, B, chw);
-    }
-    DVD_LAUNCH_CHECK();
-    if (hp) {                                                 // d(rh) = conv_o^T(da_o), h-half
-      if (wplanes) {
-        TmaOperands op;
-        op.w_hi = ws.whoT_hi; op.w_lo = ws.whoT_lo; op.CoutP = ChP;
-        if (gplanes) {
-          op.a_hi = pl_hi + t * pl_frame; op.a_lo = pl_lo + t * pl_frame;
-          op.a_Cp = G3P; op.a_c_off = 2 * Ch; op.a_img_stride = pl_img;
-        }
-        DVD_TRY(conv_fwd_ex(&d_rh, g_t + 2 * chw, ws.whoT, ws.d_rh, &op, nullptr, st));
+    if (need_k1) {
+      if (gplanes) {
+        ProfScope ps(3, "gru_bwd1", st);
+        gru_bwd1_planes_kernel<<<pgrid, 256, 0, st>>>(g_t, g_bs, hp, hp_bs, dh + (int64_t)t * h_ts, h_bs, carry_in,
+                                                       carry_out, Ch, HW, pl_hi + t * pl_frame, pl_lo + t * pl_frame,
+                                                       pl_img, G3P);
       } else {
-        DVD_TRY(dvd_conv_fwd(&d_rh, g_t + 2 * chw, ws.whoT, nullptr, nullptr, ws.d_rh, stream));
+        ProfScope ps(3, "gru_bwd1", st);
+        gru_bwd1_kernel<<<eb, 256, 0, st>>>(g_t, g_bs, hp, hp_bs, dh + (int64_t)t * h_ts, h_bs, carry_in, carry_out, B, chw);
       }
+      DVD_LAUNCH_CHECK();
     }
-    if (gplanes) {
-      ProfScope ps(3, "gru_bwd2", st);
-      gru_bwd2_planes_kernel<<<pgrid, 256, 0, st>>>(g_t, g_bs, hp, hp_bs, ws.d_rh, carry_out, Ch, HW,
-                                                     pl_hi + t * pl_frame, pl_lo + t * pl_frame, pl_img, G3P);
-    } else {
-      ProfScope ps(3, "gru_bwd2", st);
-      gru_bwd2_kernel<<<eb, 256, 0, st>>>(g_t, g_bs, hp, hp_bs, ws.d_rh, carry_out, B, chw);
-    }
-    DVD_LAUNCH_CHECK();
-    if (hp) {                                                 // dh_prev += conv_u^T(da_u) + conv_r^T(da_r)
-      if (wplanes) {
-        TmaOperands op;
-        op.w_hi = ws.whurT_hi; op.w_lo = ws.whurT_lo; op.CoutP = ChP;
-        if (gplanes) {
-          op.a_hi = pl_hi + t * pl_frame; op.a_lo = pl_lo + t * pl_frame;
-          op.a_Cp = G3P; op.a_c_off = 0; op.a_img_stride = pl_img;
-        }
-        DVD_TRY(conv_fwd_ex(&d_hp, g_t, ws.whurT, carry_out, &op, nullptr, st));
+    need_k1 = true;
+    if (hp && bptt_fused) {
+      // d(rh) = conv_o^T(da_o) with the reset-gate gradient in the epilogue (mode 3)
+      TmaOperands op;
+      op.w_hi = ws.whoT_hi; op.w_lo = ws.whoT_lo; op.CoutP = ChP;
+      op.a_hi = pl_hi + t * pl_frame; op.a_lo = pl_lo + t * pl_frame;
+      op.a_Cp = G3P; op.a_c_off = 2 * Ch; op.a_img_stride = pl_img;
+      GruEpi ge;
+      ge.mode = 3; ge.Ch = Ch; ge.hprev = hp; ge.hp_s1 = hp_bs; ge.ugate = g_t; ge.u_s1 = g_bs;
+      ge.out2 = carry_out; ge.o2_s1 = chw;
+      ge.pl_hi = pl_hi + t * pl_frame; ge.pl_lo = pl_lo + t * pl_frame; ge.pl_Cp = G3P; ge.pl_img = pl_img;
+      DVD_TRY(conv_fwd_ex(&d_rh, g_t + 2 * chw, ws.whoT, carry_out, &op, &ge, st));
+      // dh_{t-1} += conv_ur^T(da_u | da_r); for t > 0 the epilogue (mode 4) goes straight on with step t-1's part 1
+      op.w_hi = ws.whurT_hi; op.w_lo = ws.whurT_lo; op.a_c_off = 0;
+      if (t > 0) {
+        dvd_conv_desc d4 = d_hp;
+        d4.accumulate = 0;
+        GruEpi g4;
+        g4.mode = 4; g4.Ch = Ch; g4.ugate = gates + (int64_t)(t - 1) * g_ts; g4.u_s1 = g_bs;
+        g4.hprev = t > 1 ? h + (int64_t)(t - 2) * h_ts : h0; g4.hp_s1 = t > 1 ? h_bs : chw;
+        g4.carry_in = carry_out; g4.out2 = carry_next; g4.o2_s1 = chw;
+        g4.dh_prev = dh + (int64_t)(t - 1) * h_ts; g4.dh_s1 = h_bs;
+        g4.pl_hi = pl_hi + (t - 1) * pl_frame; g4.pl_lo = pl_lo + (t - 1) * pl_frame; g4.pl_Cp = G3P; g4.pl_img = pl_img;
+        DVD_TRY(conv_fwd_ex(&d4, g_t, ws.whurT, carry_next, &op, &g4, st));
+        need_k1 = false;
       } else {
-        DVD_TRY(dvd_conv_fwd(&d_hp, g_t, ws.whurT, nullptr, nullptr, carry_out, stream));
+        DVD_TRY(conv_fwd_ex(&d_hp, g_t, ws.whurT, carry_out, &op, nullptr, st));
+      }
+    } else {
+      if (hp) {                                                 // d(rh) = conv_o^T(da_o), h-half
+        if (wplanes) {
+          TmaOperands op;
+          op.w_hi = ws.whoT_hi; op.w_lo = ws.whoT_lo; op.CoutP = ChP;
+          if (gplanes) {
+            op.a_hi = pl_hi + t * pl_frame; op.a_lo = pl_lo + t * pl_frame;
+            op.a_Cp = G3P; op.a_c_off = 2 * Ch; op.a_img_stride = pl_img;
+          }
+          DVD_TRY(conv_fwd_ex(&d_rh, g_t + 2 * chw, ws.whoT, ws.d_rh, &op, nullptr, st));
+        } else {
+          DVD_TRY(dvd_conv_fwd(&d_rh, g_t + 2 * chw, ws.whoT, nullptr, nullptr, ws.d_rh, stream));
+        }
+      }
+      if (gplanes) {
+        ProfScope ps(3, "gru_bwd2", st);
+        gru_bwd2_planes_kernel<<<pgrid, 256, 0, st>>>(g_t, g_bs, hp, hp_bs, ws.d_rh, carry_out, Ch, HW,
+                                                       pl_hi + t * pl_frame, pl_lo + t * pl_frame, pl_img, G3P);
+      } else {
+        ProfScope ps(3, "gru_bwd2", st);
+        gru_bwd2_kernel<<<eb, 256, 0, st>>>(g_t, g_bs, hp, hp_bs, ws.d_rh, carry_out, B, chw);
+      }
+      DVD_LAUNCH_CHECK();
+      if (hp) {                                                 // dh_prev += conv_u^T(da_u) + conv_r^T(da_r)
+        if (wplanes) {
+          TmaOperands op;
+          op.w_hi = ws.whurT_hi; op.w_lo = ws.whurT_lo; op.CoutP = ChP;
+          if (gplanes) {
+            op.a_hi = pl_hi + t * pl_frame; op.a_lo = pl_lo + t * pl_frame;
+            op.a_Cp = G3P; op.a_c_off = 0; op.a_img_stride = pl_img;
+          }
+          DVD_TRY(conv_fwd_ex(&d_hp, g_t, ws.whurT, carry_out, &op, nullptr, st));
+        } else {
+          DVD_TRY(dvd_conv_fwd(&d_hp, g_t, ws.whurT, nullptr, nullptr, carry_out, stream));
+        }
       }
     }
     carry_in = carry_out;
-    carry_out = (carry_out == ws.carry0) ? ws.carry1 : ws.carry0;
+    carry_out = carry_next;
   }
   if (dh0) DVD_CUDA(cudaMemcpyAsync(dh0, carry_in, sizeof(float) * (size_t)B * chw, cudaMemcpyDeviceToDevice, st));
   if (share && !gplanes)

@@ -56,11 +56,16 @@ fi
 if has ncu; then
   timeout 400 ncu --set full --clock-control none --import-source on -k regex:conv_tma_ -c 4 -f -o $O/conv_tma_s9 \
       python profiles/conv_microbench.py --reps 1 --only s9_cell1_h_ur > $O/ncu_full.log 2>&1; echo "ncu full rc=$?"
-  # memory-bound kernels and attention: two launches of each family from a short step (B = 64, 4 frames)
-  timeout 600 ncu --set full --clock-control none --import-source on \
-      -k regex:"prep_planes|cbn_apply_vec|bn_partial_vec|cbn_bwd_dx_vec|attn_tc_kernel|gru_bwd1_planes" -s 40 -c 24 -f \
-      -o $O/membound python bench.py --frames 4 --steps 1 --warmup 0 --no-e2e --no-cpu-baseline \
+  # memory-bound kernels at full size (config 2, B = 64, 48 frames): only the matching launches are profiled, the rest
+  # of the step runs untouched.  -s skips the small early launches of the step.
+  timeout 900 ncu --set full --clock-control none --import-source on \
+      -k regex:"prep_planes|cbn_apply_vec|bn_partial_vec|cbn_bwd_dx_vec|cbn_bwd_plane_vec|gru_bwd1_planes|channel_sum|adam_kernel" \
+      -s 300 -c 40 -f -o $O/membound python bench.py --steps 1 --warmup 0 --no-e2e --no-cpu-baseline \
       > $O/ncu_membound.log 2>&1; echo "ncu membound rc=$?"
+  # the attention kernels at N = 4096 (config 4: Ds on 256x256 frames)
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:"attn_tc_kernel" -c 8 -f -o $O/attn \
+      python bench.py --config 4 --steps 1 --warmup 0 --no-e2e --no-cpu-baseline > $O/ncu_attn.log 2>&1; echo "ncu attn rc=$?"
+  if [ -n "$NCU_SKIP_LAUNCHES" ]; then exit 0; fi
   timeout 300 python bench.py --frames 8 --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --prof-dump $O/prof_f8.tsv \
       > $O/bench_f8.json 2> $O/bench_f8.err; echo "bench f8 rc=$?"
   timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $O/launches_f8.csv \

@@ -86,11 +86,12 @@ def test_ddp_first_step_equals_mean_of_isolated_shards(two_gpus):
         tr = Trainer(None, argparse.Namespace(**dict(CFG, dp_shard=(2, r))))
         out = tr.train_step(clips, labels)
         shard_losses.append([float(out[k]) for k in ("ds_loss", "dt_loss", "g_loss")])
-    # a rank's D losses are its own shard's (same weights, same draws); g_loss follows the averaged D updates, so it only
-    # agrees approximately (lr = 5e-5)
+    # a rank's D losses are its own shard's (same weights, same draws).  g_loss is computed after the two D updates, which
+    # in the job follow the AVERAGED gradient (beta1 = 0: every weight moves by lr * sign of it) and in isolation the
+    # shard's own: measured 1.4 % apart on this tiny network, so only a loose bound applies
     for r in range(2):
         assert res[r]["losses"][:2] == pytest.approx(shard_losses[r][:2], rel=1e-5, abs=1e-6)
-        assert res[r]["losses"][2] == pytest.approx(shard_losses[r][2], rel=1e-2, abs=1e-3)
+        assert res[r]["losses"][2] == pytest.approx(shard_losses[r][2], rel=5e-2)
     assert res[0]["losses"] != res[1]["losses"]                          # different shards of the batch
 
 

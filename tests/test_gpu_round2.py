@@ -529,3 +529,33 @@ def test_flash_attention_falls_back_outside_its_coverage(dev):
     assert lib.dvd_attn_flash_supported(2, 16, 128, 100, 96, 0) == 0        # Nq % 8
     assert lib.dvd_attn_flash_supported(2, 96, 128, 256, 256, 0) == 0       # dq > 64
     assert lib.dvd_attn_flash_supported(2, 16, 256, 256, 256, 0) == 1 and lib.dvd_attn_flash_supported(2, 16, 256, 256, 256, 1) == 0
+
+
+@pytest.mark.parametrize("with_h0", [False, True])
+def test_fused_bptt_epilogues_match_separate_kernels(dev, with_h0):
+    """option "gru_bwd_fused": the gate-gradient math of the BPTT sweep in the epilogues of the two per-step dgrad GEMMs
+    (GruEpi modes 3 / 4) against the separate elementwise kernels it replaces -- same operands, same planes."""
+    from dvdgan_b200 import _C, ops
+    B, T, Cx, Ch, H, W, k = 48, 5, 128, 128, 32, 32, 5
+    torch.manual_seed(21)
+    x = torch.randn(B, T, Cx, H, W, device=dev) * 0.7
+    h0 = torch.randn(B, Ch, H, W, device=dev) * 0.3 if with_h0 else None
+    ws = [(torch.randn(Ch, Cx + Ch, k, k, device=dev) * 0.02).requires_grad_(True) for _ in range(3)]
+    bs = [(torch.randn(Ch, device=dev) * 0.1).requires_grad_(True) for _ in range(3)]
+    wgt = torch.randn(B, T, Ch, H, W, device=dev)
+    res = {}
+    for fused in (1, 0):
+        _C.set_option("gru_bwd_fused", fused)
+        try:
+            xx = x.clone().requires_grad_(True)
+            hh = h0.clone().requires_grad_(True) if with_h0 else None
+            h = ops.GRULayerFn.apply(xx, hh, ws[0], ws[1], ws[2], bs[0], bs[1], bs[2], 0)
+            (h * wgt).sum().backward()
+            res[fused] = [xx.grad.clone()] + ([hh.grad.clone()] if with_h0 else []) + [w.grad.clone() for w in ws] + \
+                         [b.grad.clone() for b in bs]
+            for t in ws + bs:
+                t.grad = None
+        finally:
+            _C.set_option("gru_bwd_fused", 1)
+    for a, b in zip(res[1], res[0]):
+        assert rel(a, b) < 2e-5, rel(a, b)
