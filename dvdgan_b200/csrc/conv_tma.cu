@@ -284,6 +284,50 @@ __global__ void __launch_bounds__(256) prep_planes_kernel(const PrepP p) {
   }
 }
 
+// Vectorised variant for the common case (no upsample, pixel counts and strides that are multiples of 4, 16-byte aligned
+// source, no padded rows): block = 64 pixels x 64 channels, 128-bit loads along the pixel axis (256 contiguous bytes
+// per channel row and half-warp), 128-bit plane stores.
+__global__ void __launch_bounds__(256) prep_planes_vec_kernel(const PrepP p) {
+  __shared__ float tile[64][65];
+  const int n = blockIdx.z;
+  const int pix0 = blockIdx.x * 64;
+  const int c0 = blockIdx.y * 64;
+  const int n1 = n / p.N2, n2 = n - n1 * p.N2;
+  const float* src = p.src + (int64_t)n1 * p.s1 + (int64_t)n2 * p.s2;
+  const int tid = threadIdx.x;
+  {
+    const int g = tid & 15, pix = pix0 + 4 * g;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = (tid >> 4) + 16 * j;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (pix < p.in_pix && c0 + c < p.C) {
+        v = __ldg(reinterpret_cast<const float4*>(src + (int64_t)(c0 + c) * p.cs + pix));
+        if (p.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+      }
+      tile[c][4 * g] = v.x; tile[c][4 * g + 1] = v.y; tile[c][4 * g + 2] = v.z; tile[c][4 * g + 3] = v.w;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int rep = 0; rep < 2; ++rep) {
+    const int item = tid + 256 * rep;          // 64 pixels x 8 chunks of 8 channels
+    const int px = item >> 3, q = item & 7;
+    const int pix = pix0 + px;
+    if (pix < p.out_pix) {
+      float v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = tile[q * 8 + i][px];
+      uint4 h, l;
+      if (p.fp16) fp16_split8(v, &h, &l);
+      else bf16_split8(v, &h, &l);
+      const int64_t o = ((int64_t)n * p.out_pix + pix) * p.Cp + c0 + q * 8;
+      *reinterpret_cast<uint4*>(p.hi + o) = h;
+      *reinterpret_cast<uint4*>(p.lo + o) = l;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ shared pieces
 struct TileGeom {
   int bw, bh, bd, bn;      // box extents (w, h, d, images); bw*bh*bd*bn = rows per box
@@ -1075,10 +1119,12 @@ static int prep_planes(const float* src, int N1, int N2, int C, int Cp, int64_t 
   p.in_pix = in_pix; p.out_pix = out_pix; p.W = W; p.HW = HW; p.up = up; p.relu = relu; p.fp16 = fp16;
   const int N = N1 * N2;
   DVD_CHECK_ARG(N <= 65535);          // gridDim.z
-  dim3 grid(ceil_div(out_pix, 32), Cp / 64, N);
+  const bool vec = !up && in_pix == out_pix && in_pix % 4 == 0 && cs % 4 == 0 && s1 % 4 == 0 && s2 % 4 == 0 &&
+                   (reinterpret_cast<uintptr_t>(src) & 15) == 0 && out_pix >= 64;
   prof_tag("prep N%d pix%d C%d", N, out_pix, Cp);
   prof_begin(2, (double)N * out_pix * Cp * 8.0, st);          // "flops" = bytes moved (4 in + 4 out per element)
-  prep_planes_kernel<<<grid, 256, 0, st>>>(p);
+  if (vec) prep_planes_vec_kernel<<<dim3(ceil_div(out_pix, 64), Cp / 64, N), 256, 0, st>>>(p);
+  else prep_planes_kernel<<<dim3(ceil_div(out_pix, 32), Cp / 64, N), 256, 0, st>>>(p);
   prof_end(2, st);
   DVD_LAUNCH_CHECK();
   return 0;

@@ -60,11 +60,16 @@ if has ncu; then
   # of the step runs untouched.  -s skips the small early launches of the step.
   timeout 900 ncu --set full --clock-control none --import-source on \
       -k regex:"prep_planes|cbn_apply_vec|bn_partial_vec|cbn_bwd_dx_vec|cbn_bwd_plane_vec|gru_bwd1_planes|channel_sum|adam_kernel" \
-      -s 300 -c 40 -f -o $O/membound python bench.py --steps 1 --warmup 0 --no-e2e --no-cpu-baseline \
+      -s 300 -c 32 -f -o $O/membound python bench.py --steps 1 --warmup 0 --no-e2e --no-cpu-baseline \
       > $O/ncu_membound.log 2>&1; echo "ncu membound rc=$?"
   # the attention kernels at N = 4096 (config 4: Ds on 256x256 frames)
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:"attn_tc_kernel" -c 8 -f -o $O/attn \
       python bench.py --config 4 --steps 1 --warmup 0 --no-e2e --no-cpu-baseline > $O/ncu_attn.log 2>&1; echo "ncu attn rc=$?"
+  # gpurun brings back at most 64 MiB: keep the raw-page CSV exports, drop the big reports (sources included)
+  for r in membound attn; do
+    ncu -i $O/$r.ncu-rep --page raw --csv > $O/${r}_raw.csv 2>/dev/null && gzip -f $O/${r}_raw.csv && rm -f $O/$r.ncu-rep
+  done
+  ls -la $O | head -40
   if [ -n "$NCU_SKIP_LAUNCHES" ]; then exit 0; fi
   timeout 300 python bench.py --frames 8 --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --prof-dump $O/prof_f8.tsv \
       > $O/bench_f8.json 2> $O/bench_f8.err; echo "bench f8 rc=$?"

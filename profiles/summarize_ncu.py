@@ -26,7 +26,13 @@ TO_US = {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6, "nsecond": 1e-3, "usecond":
 
 
 def read(rep):
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    if rep.endswith(".csv.gz"):          # a raw-page export made on the GPU box (the report itself was too big to bring back)
+        import gzip
+        raw = gzip.open(rep, "rt").read()
+    elif rep.endswith(".csv"):
+        raw = open(rep).read()
+    else:
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units = rows[0], rows[1]
     col = {h: i for i, h in enumerate(hdr)}
