@@ -27,7 +27,9 @@ enum Option {
   OPT_GRU_FUSED,         // "gru_fused":   ConvGRU gate math in the h-half GEMM epilogues (1)
   OPT_GRU_SHARE_PLANES,  // "gru_share_planes": BPTT gate-gradient planes shared by x-dgrad and the weight gradients (1)
   OPT_GRU_BWD_PLANES,    // "gru_bwd_planes":  the BPTT elementwise kernels write those planes themselves (1)
-  OPT_GRU_BWD_FUSED,     // "gru_bwd_fused":   BPTT gate-gradient math in the per-step dgrad GEMM epilogues (1)
+  OPT_GRU_BWD_FUSED,     // "gru_bwd_fused":   BPTT gate-gradient math in the per-step dgrad GEMM epilogues (0: measured
+                         //                    neutral -- 1000 fewer launches per step, but the single accumulator set
+                         //                    cannot hide the longer epilogues, so the time only moves into the GEMMs)
   OPT_FLASH_ATTN,        // "flash_attn":  tcgen05 attention that never materialises the N x N map (1)
   OPT_FWD_BF16,          // "fwd_bf16":    bf16 operand planes in the forward too (fp32 range, 16-bit operand precision) (0)
   OPT_COUNT

@@ -867,7 +867,7 @@ namespace {
 struct OptDef { const char* name; int def; };
 const OptDef kOptDefs[OPT_COUNT] = {
     {"simt_only", 0}, {"pair", 1}, {"persist", 1}, {"oneacc", 0}, {"occ2", 1}, {"epi_prefetch", 1},
-    {"gru_fused", 1}, {"gru_share_planes", 1}, {"gru_bwd_planes", 1}, {"gru_bwd_fused", 1}, {"flash_attn", 1},
+    {"gru_fused", 1}, {"gru_share_planes", 1}, {"gru_bwd_planes", 1}, {"gru_bwd_fused", 0}, {"flash_attn", 1},
     {"fwd_bf16", 0},
 };
 std::atomic<int> g_opts[OPT_COUNT];

@@ -437,9 +437,11 @@ extern "C" int dvd_convgru_layer_bwd(const float* x, int64_t x_bs, int64_t x_ts,
     pl_hi = reinterpret_cast<__nv_bfloat16*>(gp.p);
     pl_lo = pl_hi + elems;
   }
-  // Fused BPTT: the gate-gradient math between the two dgrad GEMMs of a step, and between one step and the next, runs
-  // in their epilogues (GruEpi modes 3 / 4): two launches per step instead of four.  Only where the GEMMs fill the
-  // machine without split-K (the small early stages keep the separate kernels and their split-K dgrads).
+  // Fused BPTT (option "gru_bwd_fused", off by default): the gate-gradient math between the two dgrad GEMMs of a step,
+  // and between one step and the next, runs in their epilogues (GruEpi modes 3 / 4): two launches per step instead of
+  // four.  Only where the GEMMs fill the machine without split-K (the small early stages keep the separate kernels and
+  // their split-K dgrads).  Measured on config 2 (profiles/r2): helpers 135 -> 102 ms, fwd/dgrad GEMMs 1026 -> 1066 ms,
+  // step unchanged -- with one accumulator set per CTA pair the tensor pipe waits for the longer epilogue.
   const bool bptt_fused = gplanes && get_option(OPT_GRU_BWD_FUSED) &&
                           (int64_t)ceil_div(B * HW, 128) * ceil_div(Ch, 128) >= num_sms();
   bool need_k1 = true;        // the elementwise part 1 of this step has not been done by the previous step's epilogue

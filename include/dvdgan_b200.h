@@ -48,7 +48,8 @@ int dvd_prof_dump(const char* path);
  *                   "fwd_bf16": measured +2 % on the step, Generator output 1.2e-3 from the fp32 reference)
  *   "fwd_bf16" 0    bf16 operand planes in the forward too: fp32's exponent range at 16-bit operand precision; the
  *                   default fp16 planes (22 bits) clamp |x| > 65504 and count it (dvd_saturation_count)
- *   "gru_fused" 1, "gru_share_planes" 1, "gru_bwd_planes" 1   ConvGRU fusion levels
+ *   "gru_fused" 1, "gru_share_planes" 1, "gru_bwd_planes" 1, "gru_bwd_fused" 0   ConvGRU fusion levels (the last one
+ *                   moves the BPTT gate-gradient math into the dgrad GEMM epilogues: measured neutral, off)
  *   "flash_attn" 1  attention on the tensor cores without the N x N map (0: materialised SIMT path)
  * Unknown names are an error. */
 int dvd_set_option(const char* name, int value);

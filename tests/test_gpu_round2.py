@@ -556,6 +556,6 @@ def test_fused_bptt_epilogues_match_separate_kernels(dev, with_h0):
             for t in ws + bs:
                 t.grad = None
         finally:
-            _C.set_option("gru_bwd_fused", 1)
+            _C.set_option("gru_bwd_fused", 0)
     for a, b in zip(res[1], res[0]):
         assert rel(a, b) < 2e-5, rel(a, b)
