@@ -559,3 +559,29 @@ def test_fused_bptt_epilogues_match_separate_kernels(dev, with_h0):
             _C.set_option("gru_bwd_fused", 0)
     for a, b in zip(res[1], res[0]):
         assert rel(a, b) < 2e-5, rel(a, b)
+
+
+def test_generator_with_optional_attention_blocks(dev):
+    """Generator(attention=True) wires in the two non-local blocks the reference leaves commented out
+    (Generator.py:28-36).  Their gamma is initialised to 0 (Attention.py), so with the same weights the output is the
+    plain Generator's, while the backward pass reaches the attention parameters; the default keeps the reference's
+    state_dict key set."""
+    from dvdgan_b200.Module.Generator import Generator
+    torch.manual_seed(3)
+    G0 = Generator(in_dim=120, latent_dim=4, n_class=3, ch=8, n_frames=4)
+    torch.manual_seed(3)
+    G1 = Generator(in_dim=120, latent_dim=4, n_class=3, ch=8, n_frames=4, attention=True)
+    extra = set(G1.state_dict()) - set(G0.state_dict())
+    assert extra and all(k.startswith(("self_attn.", "sep_attn.")) for k in extra)
+    G1.load_state_dict(G0.state_dict(), strict=False)
+    z = torch.randn(2, 120)
+    cls = torch.tensor([0, 2])
+    G0.to(dev), G1.to(dev)
+    y0 = G0(z.to(dev), cls.to(dev))
+    y1 = G1(z.to(dev), cls.to(dev))
+    assert rel(y1, y0) < 1e-6
+    y1.sum().backward()
+    assert float(G1.self_attn.gamma.grad.abs()) > 0 and float(G1.sep_attn.model[0].gamma.grad.abs()) > 0
+    with torch.no_grad():           # a non-zero gamma changes the output: the blocks are really in the graph
+        G1.self_attn.gamma.fill_(0.5)
+    assert rel(G1(z.to(dev), cls.to(dev)), y0) > 1e-3
