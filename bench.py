@@ -59,6 +59,14 @@ def workload_name(a, batch_per_gpu, world):
             + (", NCCL grad all-reduce)" if world > 1 else ")"))
 
 
+def gru_policy(lean):
+    if lean is None or lean is False:
+        return "h + gates + r*h kept"
+    if lean is True or lean == 0:
+        return "h only, gates recomputed"
+    return f"h only + recomputed gates for ConvGRU layers whose full state is >= {lean / 2 ** 30:.1f} GiB, full state for the rest"
+
+
 def step_work(a):
     """(TFLOP, HBM GB) per clip and step from SURVEY 8(d), or (None, None) off the BASELINE shapes."""
     for c in CONFIGS.values():
@@ -409,8 +417,7 @@ def run_b200(a):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(a, B, world),
                        "global_batch": B * world, "l2": "inputs and activations are GBs per step (>> 126 MB L2)",
-                       "parallelism": f"dp{world}", "gru_bptt_state": "h only, gates recomputed" if tr.gru_lean
-                       else "h + gates + r*h kept", "optimizer": "sharded (RS/Adam/AG)" if a.shard_optimizer and world > 1
+                       "parallelism": f"dp{world}", "gru_bptt_state": gru_policy(tr.gru_lean), "optimizer": "sharded (RS/Adam/AG)" if a.shard_optimizer and world > 1
                        else "replicated (all-reduce + full Adam)"},
             "e2e": {"value": clips / sec_e2e, "unit": UNIT,
                     "h2d_bytes_per_step": host_clips[0].numel() * 4 + host_labels[0].numel() * 8 + B * 120 * 4 + B * 8,

@@ -205,7 +205,7 @@ def test_full_width_two_steps_vs_reference_trainer(dev):
 # ---------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("shape", [(2, 6, 64, 64, 16, 16, 3), (1, 5, 128, 64, 32, 32, 5)])
 def test_convgru_lean_bptt_matches_full_state(dev, shape):
-    """ops.GRU_LEAN keeps h only and recomputes gates / r*h at the start of the backward: same kernels on the same
+    """ops.set_gru_lean(True) keeps h only and recomputes gates / r*h at the start of the backward: same kernels on the same
     operands, so the gradients agree to summation-order noise with the run that kept the whole state."""
     from dvdgan_b200 import ops
     B, T, Cx, Ch, H, W, k = shape

@@ -53,6 +53,16 @@ def test_gru_state_estimate_drives_lean_mode():
     # config 3 (32 clips of 48 x 128x128 per GPU) does not fit 180 GB with the full state; lean does
     assert gru_state_bytes(32, 48, 32, 8, lean=False) > 0.35 * 180e9
     assert gru_state_bytes(32, 48, 32, 8, lean=True) < 25e9
+    # the policy runs only the largest layers lean: at config 3 the three layers of the 64x64 stage and the equally
+    # large middle layer of the 32x32 stage (layers of one size share the policy); the other eight keep their state
+    from dvdgan_b200.ops import gru_lean_threshold, gru_layer_state_bytes
+    thr, kept = gru_lean_threshold(32, 48, 32, 8, 0.30 * 190e9)
+    sizes = gru_layer_state_bytes(32, 48, 32, 8)
+    assert [i for i, s in enumerate(sizes) if s >= thr] == [7, 9, 10, 11] and kept <= 0.30 * 190e9
+    assert kept == sum(s // 5 if s >= thr else s for s in sizes)
+    assert gru_lean_threshold(64, 48, 32, 4, 0.30 * 190e9)[0] is None          # config 2: nothing recomputed
+    assert gru_lean_threshold(16, 128, 32, 4, 0.30 * 190e9)[0] is None         # config 5
+    assert gru_lean_threshold(32, 48, 32, 8, 1e9)[0] == 0                      # hopeless budget: everything lean
 
 
 def test_fixture_sampler_is_deterministic():
