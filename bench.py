@@ -62,9 +62,10 @@ def workload_name(a, batch_per_gpu, world):
 def gru_policy(lean):
     if lean is None or lean is False:
         return "h + gates + r*h kept"
-    if lean is True or lean == 0:
+    if lean is True:
         return "h only, gates recomputed"
-    return f"h only + recomputed gates for ConvGRU layers whose full state is >= {lean / 2 ** 30:.1f} GiB, full state for the rest"
+    return ("h only + recomputed gates for %d of the 12 ConvGRU layers (Cx,Ch,H,W,k = %s), full state for the rest"
+            % (len(lean), sorted(lean)))
 
 
 def step_work(a):

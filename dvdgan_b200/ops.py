@@ -421,31 +421,34 @@ class CBNConvFn(torch.autograd.Function):
 # ConvGRU BPTT state policy.  Full: keep the activated gates (3Ch) and r*h (Ch) of every frame next to h (Ch) -- 20
 # bytes per hidden element, nothing recomputed.  Lean: keep h only (4 bytes per hidden element) and re-run the layer's
 # forward sweep into transient buffers at the start of its backward (same kernels, same operands -> the same gate
-# values); costs one extra forward of that layer per step.  The policy is a size threshold: a layer whose FULL state is
-# at least GRU_LEAN_MIN_BYTES runs lean (None: never; 0: every layer), so that only the few largest layers pay the
-# recomputation -- which is what lets 128x128 clips at 32 per GPU fit 180 GB at +12 % instead of +25 % step time.
-GRU_LEAN_MIN_BYTES = None
+# values); costs one extra forward of that layer per step.  The policy is per layer: GRU_LEAN is False (never), True
+# (every layer) or a set of layer signatures (Cx, Ch, H, W, k) chosen by ``gru_lean_policy`` so that the layers that
+# free the most bytes per recomputed FLOP go lean first -- which is what lets 128x128 clips at 32 per GPU fit 180 GB
+# at +8 % step time instead of +25 %.
+GRU_LEAN = False
 
 
-def set_gru_lean(flag):
-    """False / None: full state everywhere; True: lean everywhere; an int: lean for layers whose full state is at least
-    that many bytes."""
-    global GRU_LEAN_MIN_BYTES
-    if flag is None or flag is False:
-        GRU_LEAN_MIN_BYTES = None
-    elif flag is True:
-        GRU_LEAN_MIN_BYTES = 0
-    else:
-        GRU_LEAN_MIN_BYTES = int(flag)
+def set_gru_lean(policy):
+    """False / None: full state everywhere; True: lean everywhere; a set of (Cx, Ch, H, W, k): lean for those layers."""
+    global GRU_LEAN
+    GRU_LEAN = False if policy is None else (policy if isinstance(policy, bool) else frozenset(policy))
+
+
+def gru_layers(ch, latent_dim):
+    """(Cx, Ch, H, W, k) of the Generator's 12 ConvGRU layers in order (Generator.py:38-52)"""
+    out = []
+    for stage, side in enumerate((latent_dim, 2 * latent_dim, 4 * latent_dim, 8 * latent_dim)):
+        hs, ks = ((4 * ch, 8 * ch, 4 * ch), (3, 5, 5)) if stage == 3 else ((8 * ch, 16 * ch, 8 * ch), (3, 5, 3))
+        cx = hs[0]
+        for h, k in zip(hs, ks):
+            out.append((cx, h, side, side, k))
+            cx = h
+    return out
 
 
 def gru_layer_state_bytes(B, T, ch, latent_dim):
-    """full-state bytes (20 per hidden element) of the Generator's 12 ConvGRU layers (Generator.py:38-52)"""
-    out = []
-    for stage, side in enumerate((latent_dim, 2 * latent_dim, 4 * latent_dim, 8 * latent_dim)):
-        for hidden in ((4 * ch, 8 * ch, 4 * ch) if stage == 3 else (8 * ch, 16 * ch, 8 * ch)):
-            out.append(B * T * hidden * side * side * 20)
-    return out
+    """full-state bytes (20 per hidden element) of those layers"""
+    return [B * T * Ch * H * W * 20 for (_, Ch, H, W, _) in gru_layers(ch, latent_dim)]
 
 
 def gru_state_bytes(B, T, ch, latent_dim, lean):
@@ -453,19 +456,24 @@ def gru_state_bytes(B, T, ch, latent_dim, lean):
     return sum(gru_layer_state_bytes(B, T, ch, latent_dim)) // (5 if lean else 1)
 
 
-def gru_lean_threshold(B, T, ch, latent_dim, budget_bytes):
-    """Smallest set of the largest layers to run lean so that the kept ConvGRU state fits ``budget_bytes``:
-    -> (threshold for set_gru_lean or None, bytes kept under that policy)."""
-    sizes = sorted(gru_layer_state_bytes(B, T, ch, latent_dim), reverse=True)
+def gru_lean_policy(B, T, ch, latent_dim, budget_bytes):
+    """Which layers keep h only so that the kept ConvGRU state fits ``budget_bytes``: greedy by bytes freed (4/5 of the
+    full state) per FLOP of the forward sweep that has to be repeated ((Cx + Ch) * Ch * k^2 per hidden-state pixel).
+    -> (policy for set_gru_lean, bytes kept under it)."""
+    layers = gru_layers(ch, latent_dim)
+    sizes = gru_layer_state_bytes(B, T, ch, latent_dim)
     kept = sum(sizes)
     if kept <= budget_bytes:
-        return None, kept
-    for i, s_ in enumerate(sizes):
-        kept -= s_ - s_ // 5
-        nxt = sizes[i + 1] if i + 1 < len(sizes) else 0
-        if kept <= budget_bytes and nxt < s_:          # layers of equal size share the policy
-            return s_, kept
-    return 0, kept
+        return False, kept
+    order = sorted(range(len(layers)), key=lambda i: -(sizes[i] * 0.8) /
+                   ((layers[i][0] + layers[i][1]) * layers[i][1] * layers[i][4] ** 2 * layers[i][2] * layers[i][3]))
+    chosen = set()
+    for i in order:
+        chosen.add(layers[i])
+        kept -= sizes[i] - sizes[i] // 5
+        if kept <= budget_bytes:
+            return chosen, kept
+    return True, kept
 
 
 class GRULayerFn(torch.autograd.Function):
@@ -502,7 +510,7 @@ class GRULayerFn(torch.autograd.Function):
         cfg = (B, T, Cx, Ch, H, W, k, x_bs, x_ts, T_bcast)
         gates, h, rh = GRULayerFn._run_fwd(x, h0, wu, wr, wo, bu, br, bo, cfg)
         # (grad mode is always off inside Function.forward: do not test it here)
-        ctx.lean = GRU_LEAN_MIN_BYTES is not None and 20 * B * T * Ch * H * W >= GRU_LEAN_MIN_BYTES
+        ctx.lean = GRU_LEAN is True or (GRU_LEAN is not False and (Cx, Ch, H, W, k) in GRU_LEAN)
         if ctx.lean:
             ctx.save_for_backward(x, h0, wu, wr, wo, bu, br, bo, h)        # gates / rh are dropped here
         else:

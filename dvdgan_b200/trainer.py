@@ -287,11 +287,11 @@ class Trainer(object):
         ops.set_sync_bn(True if (getattr(c, "sync_bn", False) and self.distributed) else None)
         lean = getattr(c, "gru_lean", "auto")
         if lean == "auto":      # full BPTT state (20 B per hidden element) while it stays under ~30 % of the device;
-            # beyond that the largest layers keep h only and recompute their gates (ops.gru_lean_threshold)
+            # beyond that the layers that free the most memory per recomputed FLOP keep h only (ops.gru_lean_policy)
             budget = 0.30 * torch.cuda.get_device_properties(self.device).total_memory
-            lean, self.gru_state_kept = ops.gru_lean_threshold(self.local_batch, self.n_frames, self.g_chn,
-                                                               self.latent_dim, budget)
-        self.gru_lean = lean if (lean is None or isinstance(lean, bool)) else int(lean)
+            lean, self.gru_state_kept = ops.gru_lean_policy(self.local_batch, self.n_frames, self.g_chn,
+                                                            self.latent_dim, budget)
+        self.gru_lean = lean
         ops.set_gru_lean(self.gru_lean)
         self.writer = None
         if self.use_tensorboard:

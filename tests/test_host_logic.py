@@ -53,16 +53,18 @@ def test_gru_state_estimate_drives_lean_mode():
     # config 3 (32 clips of 48 x 128x128 per GPU) does not fit 180 GB with the full state; lean does
     assert gru_state_bytes(32, 48, 32, 8, lean=False) > 0.35 * 180e9
     assert gru_state_bytes(32, 48, 32, 8, lean=True) < 25e9
-    # the policy runs only the largest layers lean: at config 3 the three layers of the 64x64 stage and the equally
-    # large middle layer of the 32x32 stage (layers of one size share the policy); the other eight keep their state
-    from dvdgan_b200.ops import gru_lean_threshold, gru_layer_state_bytes
-    thr, kept = gru_lean_threshold(32, 48, 32, 8, 0.30 * 190e9)
-    sizes = gru_layer_state_bytes(32, 48, 32, 8)
-    assert [i for i, s in enumerate(sizes) if s >= thr] == [7, 9, 10, 11] and kept <= 0.30 * 190e9
-    assert kept == sum(s // 5 if s >= thr else s for s in sizes)
-    assert gru_lean_threshold(64, 48, 32, 4, 0.30 * 190e9)[0] is None          # config 2: nothing recomputed
-    assert gru_lean_threshold(16, 128, 32, 4, 0.30 * 190e9)[0] is None         # config 5
-    assert gru_lean_threshold(32, 48, 32, 8, 1e9)[0] == 0                      # hopeless budget: everything lean
+    # the policy: layers that free the most bytes per recomputed FLOP go lean first, until the kept state fits
+    from dvdgan_b200.ops import gru_lean_policy, gru_layer_state_bytes, gru_layers
+    budget = 0.30 * 190e9
+    pol, kept = gru_lean_policy(32, 48, 32, 8, budget)
+    layers, sizes = gru_layers(32, 8), gru_layer_state_bytes(32, 48, 32, 8)
+    assert kept <= budget and kept == sum(s // 5 if l in pol else s for l, s in zip(layers, sizes))
+    flops = lambda l: (l[0] + l[1]) * l[1] * l[4] ** 2 * l[2] * l[3]
+    # cheaper than recomputing everything, and the expensive 5x5 middle layer of the 32x32 stage keeps its state
+    assert sum(flops(l) for l in pol) < 0.6 * sum(flops(l) for l in layers) and (256, 512, 32, 32, 5) not in pol
+    assert gru_lean_policy(64, 48, 32, 4, budget)[0] is False           # config 2: nothing recomputed
+    assert gru_lean_policy(16, 128, 32, 4, budget)[0] is False          # config 5
+    assert gru_lean_policy(32, 48, 32, 8, 1e9)[0] is True               # hopeless budget: everything lean
 
 
 def test_fixture_sampler_is_deterministic():
