@@ -1,7 +1,8 @@
 """ConvGRUCell / ConvGRU with the reference's signatures and state_dict keys (reference
 Module/ConvGRU.py:5-133).  A whole clip runs through ``ConvGRU.forward_sequence`` (one library call per
 layer: batched x-half implicit GEMM + the sequential h-half loop on the device); the per-step ``forward``
-of the reference is kept for drop-in use."""
+of the reference is kept for drop-in use.  Stacks whose layers all keep their full state run as a wavefront: layer l
+on stream l, a chunk of frames behind layer l-1 (``ops.GRUStackFn``)."""
 import torch
 import torch.nn as nn
 from torch.nn import init
@@ -75,6 +76,17 @@ class ConvGRU(nn.Module):
     def forward_sequence(self, x, T_bcast=0):
         """The Generator's frame loop (Generator.py:87-106) in one go: the last layer's hidden state for
         every frame, (B,T,C_last,H,W), from zero initial state."""
+        if T_bcast:
+            B, _, H, W = x.shape
+            T = T_bcast
+        else:
+            B, T, _, H, W = x.shape
+        sigs = [(c.input_size, c.hidden_size, H, W, c.update_gate.kernel_size[0]) for c in self.cells]
+        chunk = ops.gru_wavefront_chunk(B, T, sigs)
+        if chunk:          # the layers as a wavefront over chunks of frames, one stream per layer (ops.GRUStackFn)
+            params = [p for c in self.cells for p in (c.update_gate.weight, c.reset_gate.weight, c.out_gate.weight,
+                                                      c.update_gate.bias, c.reset_gate.bias, c.out_gate.bias)]
+            return ops.GRUStackFn.apply(x, T_bcast, chunk, *params)
         h = self.cells[0].sequence(x, None, T_bcast)
         for i in range(1, self.n_layers):
             h = self.cells[i].sequence(h)

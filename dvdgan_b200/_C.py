@@ -44,6 +44,10 @@ _SIGS = {
     "dvd_convgru_layer_workspace_bytes": (Z, [I, I, I, I, I, I, I]),
     "dvd_convgru_layer_fwd": (I, [P, L, L, P, P, P, P, P, P, P, P, P, P, I, I, I, I, I, I, I, P, Z, P]),
     "dvd_convgru_layer_bwd": (I, [P, L, L, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, I, I, I, I, I, I, I, P, Z, P]),
+    "dvd_convgru_layer_range_workspace_bytes": (Z, [I, I, I, I, I, I, I]),
+    "dvd_convgru_layer_fwd_range": (I, [P, L, L, P, P, P, P, P, P, P, P, P, P, I, I, I, I, I, I, I, I, I, P, Z, P]),
+    "dvd_convgru_layer_bwd_range": (I, [P, L, L, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, I, I, I, I, I, I, I, I, I,
+                                        P, Z, P]),
     "dvd_specnorm_fwd": (I, [P, I, I, P, P, P, P, P]),
     "dvd_specnorm_bwd": (I, [P, P, P, P, P, I, I, P, I, P, P]),
     "dvd_bn_stats": (I, [P, I, I, I, I, F, F, P, P, P, P, P, P, P]),

@@ -32,6 +32,9 @@ enum Option {
                          //                    cannot hide the longer epilogues, so the time only moves into the GEMMs)
   OPT_FLASH_ATTN,        // "flash_attn":  tcgen05 attention that never materialises the N x N map (1)
   OPT_FWD_BF16,          // "fwd_bf16":    bf16 operand planes in the forward too (fp32 range, 16-bit operand precision) (0)
+  OPT_GRU_STREAMS,       // "gru_streams": the ConvGRU time loops run as this many independent chains over batch slices,
+                         //                chain 0 on the caller's stream, the others on library-owned helper streams
+                         //                forked from / joined to it (1 = one chain, no helper streams) (2)
   OPT_COUNT
 };
 int get_option(int opt);

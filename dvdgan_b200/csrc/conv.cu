@@ -868,7 +868,7 @@ struct OptDef { const char* name; int def; };
 const OptDef kOptDefs[OPT_COUNT] = {
     {"simt_only", 0}, {"pair", 1}, {"persist", 1}, {"oneacc", 0}, {"occ2", 1}, {"epi_prefetch", 1},
     {"gru_fused", 1}, {"gru_share_planes", 1}, {"gru_bwd_planes", 1}, {"gru_bwd_fused", 0}, {"flash_attn", 1},
-    {"fwd_bf16", 0},
+    {"fwd_bf16", 0}, {"gru_streams", 2},
 };
 std::atomic<int> g_opts[OPT_COUNT];
 std::atomic<bool> g_opts_init{false};
@@ -916,18 +916,10 @@ extern "C" int dvd_saturation_count(unsigned int* count, int reset, void* stream
   return dvd::tma_saturation_count(count, reset, dvd::as_stream(stream));
 }
 
-// High-water mark (bytes) of the current device's default stream-ordered memory pool: the operand planes of the
-// tensor-core engine live there (cudaMallocAsync), next to whatever allocator the caller uses for its tensors.
+// Bytes of the library's stream-ordered scratch pools on the current device (one pool per stream that has run a
+// tensor-core GEMM): the operand planes live there (cudaMallocFromPoolAsync), next to whatever allocator the caller uses
+// for its tensors.  high_water = sum of the pools' used-memory high-water marks, reserved = what they hold right now.
 extern "C" int dvd_scratch_bytes(long long* high_water, long long* reserved) {
   DVD_CHECK_ARG(high_water != nullptr && reserved != nullptr);
-  int dev = 0;
-  DVD_CUDA(cudaGetDevice(&dev));
-  cudaMemPool_t pool;
-  DVD_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
-  uint64_t hw = 0, res = 0;
-  DVD_CUDA(cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemHigh, &hw));
-  DVD_CUDA(cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &res));
-  *high_water = (long long)hw;
-  *reserved = (long long)res;
-  return 0;
+  return dvd::tma_scratch_stats(high_water, reserved);
 }

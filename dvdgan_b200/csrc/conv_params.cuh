@@ -74,9 +74,10 @@ int tma_split_activations(const float* x, int N, int C, int64_t n_stride, int64_
 bool tma_forward_planes_fp16();   // forward operands use fp16 planes (default; options "fwd_bf16" / "oneacc" turn it off)
 int tma_saturation_count(unsigned int* count, int reset, cudaStream_t st);
 inline int tma_round64(int c) { return (c + 63) / 64 * 64; }
-// stream-ordered scratch (cudaMallocAsync pool of the engine); free with tma_scratch_free on the same stream
+// stream-ordered scratch (the engine's per-stream cudaMallocAsync pools); free with tma_scratch_free on the same stream
 int tma_scratch_alloc(void** p, size_t bytes, cudaStream_t st);
 void tma_scratch_free(void* p, cudaStream_t st);
+int tma_scratch_stats(long long* high_water, long long* reserved);
 
 // Pre-split dY planes for the weight-gradient engine: bf16 (hi, lo) planes [clips*T][D*H*W][Cp] of a (clips, T, C)
 // tensor; the conv's dY is channels [c_off, c_off + Cout) of frames [t_off, t_off + d.N2) of every clip (d.N1 clips).

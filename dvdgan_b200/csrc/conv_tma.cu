@@ -36,6 +36,7 @@
 
 #include <algorithm>
 #include <mutex>
+#include <vector>
 
 #include "common.cuh"
 #include "conv_params.cuh"
@@ -1086,24 +1087,46 @@ static bool tile_geom(int rows, int N, int D, int H, int W, TileGeom* g) {
 
 static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 
-// Stream-ordered scratch for the operand planes of one call (cudaMallocAsync from the device's default pool; the pool
-// keeps freed blocks, dvd_scratch_bytes() reports its high-water mark so that callers can account for it).
+// Stream-ordered scratch for the operand planes of one call: cudaMallocFromPoolAsync from a memory pool the library
+// keeps PER (device, stream).  One shared pool served a single stream well, but with the ConvGRU layers on one stream
+// each (and the batch chains on helper streams) blocks freed on one stream are not reusable on another until that free
+// has been reached, so a shared pool kept growing by fresh driver allocations at timing-dependent moments in the middle
+// of a step (measured: the same configuration 964 or 1394 ms per step).  A pool per stream re-uses its own blocks in
+// stream order: after the first step nothing is allocated from the driver.  The pools keep what they were given
+// (release threshold = max); dvd_scratch_bytes() reports the sum of their high-water marks.
+struct PoolEntry { int dev; cudaStream_t st; cudaMemPool_t pool; };
+static std::mutex g_pool_mu;
+static std::vector<PoolEntry> g_pools;
+
+static int scratch_pool(cudaStream_t s, cudaMemPool_t* out) {
+  int dev = 0;
+  DVD_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  for (const PoolEntry& e : g_pools)
+    if (e.dev == dev && e.st == s) { *out = e.pool; return 0; }
+  cudaMemPoolProps props;
+  memset(&props, 0, sizeof(props));
+  props.allocType = cudaMemAllocationTypePinned;
+  props.handleTypes = cudaMemHandleTypeNone;
+  props.location.type = cudaMemLocationTypeDevice;
+  props.location.id = dev;
+  cudaMemPool_t pool;
+  DVD_CUDA(cudaMemPoolCreate(&pool, &props));
+  uint64_t thr = UINT64_MAX;
+  DVD_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+  g_pools.push_back({dev, s, pool});
+  *out = pool;
+  return 0;
+}
+
 struct Scratch {
   void* ptr = nullptr;
   cudaStream_t st;
   int alloc(size_t bytes, cudaStream_t s) {
     st = s;
-    static std::atomic<uint64_t> pool_set{0};         // per device
-    if (!device_bit_test_and_set(pool_set)) {
-      int dev = 0;
-      cudaGetDevice(&dev);
-      cudaMemPool_t pool;
-      if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-        uint64_t thr = UINT64_MAX;
-        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
-      }
-    }
-    DVD_CUDA(cudaMallocAsync(&ptr, bytes, s));
+    cudaMemPool_t pool;
+    DVD_TRY(scratch_pool(s, &pool));
+    DVD_CUDA(cudaMallocFromPoolAsync(&ptr, bytes, pool, s));
     return 0;
   }
   ~Scratch() {
@@ -1362,6 +1385,24 @@ int tma_scratch_alloc(void** p, size_t bytes, cudaStream_t st) {
 }
 void tma_scratch_free(void* p, cudaStream_t st) {
   if (p) cudaFreeAsync(p, st);
+}
+// sums over the scratch pools of the current device: high-water marks of used memory, memory currently reserved
+int tma_scratch_stats(long long* high_water, long long* reserved) {
+  int dev = 0;
+  DVD_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lk(tma::g_pool_mu);
+  long long hw = 0, res = 0;
+  for (const tma::PoolEntry& e : tma::g_pools) {
+    if (e.dev != dev) continue;
+    uint64_t a = 0, b = 0;
+    DVD_CUDA(cudaMemPoolGetAttribute(e.pool, cudaMemPoolAttrUsedMemHigh, &a));
+    DVD_CUDA(cudaMemPoolGetAttribute(e.pool, cudaMemPoolAttrReservedMemCurrent, &b));
+    hw += (long long)a;
+    res += (long long)b;
+  }
+  *high_water = hw;
+  *reserved = res;
+  return 0;
 }
 int tma_split_gradients(const float* g, int N, int C, int64_t n_stride, int64_t c_stride, int pix, void* hi, void* lo,
                         cudaStream_t st) {

@@ -211,10 +211,13 @@ struct GruWs {
   uint16_t *hpl_hi[2], *hpl_lo[2];                    // planes of h_{t-1} / h_t (ping-pong), [B*HW][ChP]
   uint16_t *rhpl_hi, *rhpl_lo;                        // planes of r * h_{t-1}
   uint16_t *whoT_hi, *whoT_lo, *whurT_hi, *whurT_lo;  // backward: [taps][ChP][ChP] / [taps][ChP][round64(2Ch)]
+  uint16_t* gplanes;                                  // frame-range API only: (hi | lo) planes of the gate gradients
   size_t bytes;
 };
 
-static GruWs carve(void* base, int B, int Cx, int Ch, int HW, int taps, bool bwd) {
+// T > 0: also room for the bf16 planes [B*T][HW][round64(3Ch)] x (hi, lo) of the pre-activation gradients, which the
+// whole-clip entry point takes from the stream-ordered scratch pool but a sweep spread over several calls keeps here
+static GruWs carve(void* base, int B, int Cx, int Ch, int HW, int taps, bool bwd, int T = 0) {
   GruWs w;
   char* p = reinterpret_cast<char*>(base);
   size_t off = 0;
@@ -249,6 +252,7 @@ static GruWs carve(void* base, int B, int Cx, int Ch, int HW, int taps, bool bwd
     } else {
       w.whoT_hi = w.whoT_lo = w.whurT_hi = w.whurT_lo = nullptr;
     }
+    w.gplanes = T > 0 ? take16(2 * (size_t)B * T * HW * tma_round64(3 * Ch) + 128) : nullptr;
   }
   w.bytes = off;
   return w;
@@ -265,6 +269,78 @@ static dvd_conv_desc base_desc(int B, int T, int Cin, int Cout, int H, int W, in
   return d;
 }
 
+// ---- batch slices of the time loop as independent chains on helper streams (option "gru_streams").
+// The two GEMMs of a time step depend on each other, so one layer's loop is a chain of launches that each leave the
+// tail of their last wave of tiles empty (256 pair-tiles on 74 SM pairs = 3.46 waves) and expose their epilogues.  The
+// clips of a batch do not interact inside a ConvGRU, so the loop runs as `ns` chains over B / ns clips each: while one
+// chain's kernel drains, the CTAs of the other chain's kernel take the free SMs, and the elementwise kernels of the BPTT
+// sweep overlap the other chain's GEMMs.  Chain 0 stays on the caller's stream; chains 1.. run on library-owned
+// non-blocking streams (per host thread and device) that are forked from / joined to the caller's stream with events,
+// so the call keeps its stream-ordered semantics.
+constexpr int kMaxSlices = 4;
+struct HelperStreams {
+  cudaStream_t s[kMaxSlices - 1] = {nullptr, nullptr, nullptr};
+  cudaEvent_t fork = nullptr;
+  cudaEvent_t join[kMaxSlices - 1] = {nullptr, nullptr, nullptr};
+  bool ready = false;
+};
+static HelperStreams* helper_streams() {
+  static thread_local HelperStreams per_dev[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  HelperStreams& h = per_dev[dev];
+  if (!h.ready) {
+    if (cudaEventCreateWithFlags(&h.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    for (int i = 0; i < kMaxSlices - 1; ++i) {
+      if (cudaStreamCreateWithFlags(&h.s[i], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+      if (cudaEventCreateWithFlags(&h.join[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    }
+    h.ready = true;
+  }
+  return &h;
+}
+
+class SliceFork {
+ public:
+  SliceFork(cudaStream_t main_stream, int n) : main_(main_stream), n_(n) {}
+  ~SliceFork() { if (open_) end(); }
+  int begin() {           // everything queued on the caller's stream so far happens before the helper chains
+    if (n_ <= 1) return 0;
+    hs_ = helper_streams();
+    if (!hs_) return fail("cannot create the helper streams%s (%s:%d)", "", __FILE__, __LINE__);
+    DVD_CUDA(cudaEventRecord(hs_->fork, main_));
+    for (int i = 0; i < n_ - 1; ++i) DVD_CUDA(cudaStreamWaitEvent(hs_->s[i], hs_->fork, 0));
+    open_ = true;
+    return 0;
+  }
+  cudaStream_t stream(int i) const { return i == 0 ? main_ : hs_->s[i - 1]; }
+  int end() {             // the caller's stream continues after every chain
+    if (!open_) return 0;
+    open_ = false;
+    for (int i = 0; i < n_ - 1; ++i) {
+      DVD_CUDA(cudaEventRecord(hs_->join[i], hs_->s[i]));
+      DVD_CUDA(cudaStreamWaitEvent(main_, hs_->join[i], 0));
+    }
+    return 0;
+  }
+
+ private:
+  cudaStream_t main_;
+  int n_;
+  HelperStreams* hs_ = nullptr;
+  bool open_ = false;
+};
+
+// number of chains: the option, lowered until it divides the batch and the sliced GEMMs stay on the tensor path
+template <typename Ok>
+static int pick_slices(int B, int T, Ok ok) {
+  int ns = get_option(OPT_GRU_STREAMS);
+  if (ns > kMaxSlices) ns = kMaxSlices;
+  if (T <= 1 || ns < 1) ns = 1;
+  while (ns > 1 && (B % ns != 0 || !ok(B / ns))) --ns;
+  return ns;
+}
+
 }  // namespace dvd
 
 using namespace dvd;
@@ -273,20 +349,27 @@ extern "C" size_t dvd_convgru_layer_workspace_bytes(int B, int T, int Cx, int Ch
   (void)T;
   return carve(nullptr, B, Cx, Ch, H * W, k * k, true).bytes + 256;
 }
+extern "C" size_t dvd_convgru_layer_range_workspace_bytes(int B, int T, int Cx, int Ch, int H, int W, int k) {
+  return carve(nullptr, B, Cx, Ch, H * W, k * k, true, T).bytes + 256;
+}
 
-extern "C" int dvd_convgru_layer_fwd(const float* x, int64_t x_bs, int64_t x_ts, const float* h0, const float* wu,
-                                     const float* wr, const float* wo, const float* bu, const float* br,
-                                     const float* bo, float* gates, float* h, float* rh, int B, int T, int Cx, int Ch,
-                                     int H, int W, int k, void* workspace, size_t ws_bytes, void* stream) {
+// Frames [t0, t1) of the forward sweep.  range = false: the whole clip in one call (t0 = 0, t1 = T).  range = true: one
+// of several calls that share `workspace` and visit the frames in order -- the call with t0 = 0 packs / splits the
+// weights into the workspace, later calls find them (and the operand planes of h_{t0-1}) there.
+static int gru_fwd_impl(const float* x, int64_t x_bs, int64_t x_ts, const float* h0, const float* wu, const float* wr,
+                        const float* wo, const float* bu, const float* br, const float* bo, float* gates, float* h,
+                        float* rh, int B, int T, int Cx, int Ch, int H, int W, int k, int t0, int t1, bool range,
+                        void* workspace, size_t ws_bytes, void* stream) {
   DVD_CHECK_ARG(x && wu && wr && wo && bu && br && bo && gates && h && rh && workspace);
   DVD_CHECK_ARG(B > 0 && T > 0 && Cx > 0 && Ch > 0 && H > 0 && W > 0 && (k & 1));
+  DVD_CHECK_ARG(0 <= t0 && t0 < t1 && t1 <= T);
   const int HW = H * W, taps = k * k, Ct = Cx + Ch;
   GruWs ws = carve(workspace, B, Cx, Ch, HW, taps, false);
   DVD_CHECK_ARG(ws.bytes <= ws_bytes);
   cudaStream_t st = as_stream(stream);
   const float* wsrc[3] = {wu, wr, wo};
   const float* bsrc[3] = {bu, br, bo};
-  for (int g = 0; g < 3; ++g) {
+  for (int g = 0; g < 3 && t0 == 0; ++g) {
     DVD_TRY(dvd_weight_pack(wsrc[g], Ct, taps, 0, Ch, 0, Cx, nullptr, 0, ws.wx, Cx, 0, 3 * Ch, g * Ch, stream));
     if (g < 2) DVD_TRY(dvd_weight_pack(wsrc[g], Ct, taps, 0, Ch, Cx, Ch, nullptr, 0, ws.whur, Ch, 0, 2 * Ch, g * Ch, stream));
     else DVD_TRY(dvd_weight_pack(wsrc[g], Ct, taps, 0, Ch, Cx, Ch, nullptr, 0, ws.who, Ch, 0, Ch, 0, stream));
@@ -294,24 +377,35 @@ extern "C" int dvd_convgru_layer_fwd(const float* x, int64_t x_bs, int64_t x_ts,
   }
   const int64_t chw = (int64_t)Ch * HW;
   const int64_t g_ts = 3 * chw, g_bs = (int64_t)T * g_ts, h_ts = chw, h_bs = (int64_t)T * chw;
-  // x-halves of all gates, all frames: one implicit GEMM
+  // x-halves of all gates, all frames of the range: one implicit GEMM
   {
-    dvd_conv_desc d = base_desc(B, T, Cx, 3 * Ch, H, W, k); d.x_kind = 1;
+    dvd_conv_desc d = base_desc(B, t1 - t0, Cx, 3 * Ch, H, W, k); d.x_kind = 1;
     d.x_s1 = x_bs; d.x_s2 = x_ts; d.y_s1 = g_bs; d.y_s2 = g_ts;
-    DVD_TRY(dvd_conv_fwd(&d, x, ws.wx, ws.bias, nullptr, gates, stream));
+    DVD_TRY(dvd_conv_fwd(&d, x + (int64_t)t0 * x_ts, ws.wx, ws.bias, nullptr, gates + (int64_t)t0 * g_ts, stream));
   }
-  const int eb = ew_blocks((int64_t)B * chw);
   // Fused path: the two h-half GEMMs of a step run on the TMA/tcgen05 engine with the gate math in their epilogues
   // (update|reset: sigmoid, r*h;  out: tanh, state update) which also emit the operand planes the next GEMM reads, and the
   // h-half weight planes are split once per layer instead of once per step.
-  dvd_conv_desc d_ur = base_desc(B, 1, Ch, 2 * Ch, H, W, k), d_o = base_desc(B, 1, Ch, Ch, H, W, k);
-  d_ur.x_kind = d_o.x_kind = 1; d_ur.accumulate = d_o.accumulate = 1;
-  d_ur.y_s1 = d_o.y_s1 = g_bs; d_ur.x_s1 = d_o.x_s1 = chw;
+  auto step_descs = [&](int Bn, dvd_conv_desc* ur, dvd_conv_desc* o) {
+    *ur = base_desc(Bn, 1, Ch, 2 * Ch, H, W, k); *o = base_desc(Bn, 1, Ch, Ch, H, W, k);
+    ur->x_kind = o->x_kind = 1; ur->accumulate = o->accumulate = 1;
+    ur->y_s1 = o->y_s1 = g_bs; ur->x_s1 = o->x_s1 = chw;
+  };
+  dvd_conv_desc d_ur, d_o;
+  const bool can_fuse = gru_fused_enabled() && T > 1 && Ch % 32 == 0;
+  // chains over batch slices (see SliceFork): only where every slice stays on the fused tensor path; a caller of the
+  // frame-range API overlaps whole layers instead
+  const int ns = range ? 1 : pick_slices(B, T, [&](int Bn) {
+    step_descs(Bn, &d_ur, &d_o);
+    return can_fuse && conv_fwd_ex_eligible(&d_ur) && conv_fwd_ex_eligible(&d_o);
+  });
+  const int Bn = B / ns;
+  step_descs(Bn, &d_ur, &d_o);
+  const int eb = ew_blocks((int64_t)Bn * chw);
   const int ChP = tma_round64(Ch), Co2P = tma_round64(2 * Ch);
-  const bool fused = gru_fused_enabled() && T > 1 && Ch % 32 == 0 && conv_fwd_ex_eligible(&d_ur) &&
-                     conv_fwd_ex_eligible(&d_o);
+  const bool fused = can_fuse && conv_fwd_ex_eligible(&d_ur) && conv_fwd_ex_eligible(&d_o);
   const int f16 = tma_forward_planes_fp16() ? 1 : 0;       // the epilogues write the step-to-step planes in this format
-  if (fused) {
+  if (fused && t0 == 0) {
     DVD_TRY(tma_split_weights(ws.whur, taps, Ch, 2 * Ch, Co2P, f16, ws.whur_hi, ws.whur_lo, st));
     DVD_TRY(tma_split_weights(ws.who, taps, Ch, Ch, ChP, f16, ws.who_hi, ws.who_lo, st));
     if (ChP != Ch) {      // padded channels of the planes the epilogues write stay zero
@@ -324,80 +418,124 @@ extern "C" int dvd_convgru_layer_fwd(const float* x, int64_t x_bs, int64_t x_ts,
       DVD_CUDA(cudaMemsetAsync(ws.rhpl_lo, 0, pl, st));
     }
   }
-  bool have_planes = false;       // planes of h_{t-1} already sit in slot (t-1) & 1
-  for (int t = 0; t < T; ++t) {
-    const float* hp = t > 0 ? h + (int64_t)(t - 1) * h_ts : h0;
+  SliceFork fk(st, ns);
+  DVD_TRY(fk.begin());
+  // planes of h_{t-1} already sit in slot (t-1) & 1: written by the epilogue of step t-1 (a fused step, i.e. one with a
+  // previous state), possibly in the previous call
+  bool have_planes = fused && t0 > 0 && (t0 > 1 || h0);
+  for (int t = t0; t < t1; ++t) {
+    const bool first = t == 0 && !h0;      // zero previous state
     const int64_t hp_bs = t > 0 ? h_bs : chw;
-    float* g_t = gates + (int64_t)t * g_ts;
-    float* rh_t = rh + (int64_t)t * h_ts;
-    if (fused && hp) {
-      const int sp = (t + 1) & 1, sn = t & 1;          // slots of h_{t-1} and h_t
-      if (!have_planes)
-        DVD_TRY(tma_split_activations(hp, B, Ch, hp_bs, HW, HW, f16, ws.hpl_hi[sp], ws.hpl_lo[sp], st));
-      TmaOperands op;
-      GruEpi ge;
-      op.a_hi = ws.hpl_hi[sp]; op.a_lo = ws.hpl_lo[sp]; op.w_hi = ws.whur_hi; op.w_lo = ws.whur_lo; op.CoutP = Co2P;
-      ge.mode = 1; ge.Ch = Ch; ge.hprev = hp; ge.hp_s1 = hp_bs; ge.out2 = rh_t; ge.o2_s1 = h_bs;
-      ge.pl_hi = ws.rhpl_hi; ge.pl_lo = ws.rhpl_lo; ge.pl_Cp = ChP;
-      DVD_TRY(conv_fwd_ex(&d_ur, nullptr, nullptr, g_t, &op, &ge, st));
-      op.a_hi = ws.rhpl_hi; op.a_lo = ws.rhpl_lo; op.w_hi = ws.who_hi; op.w_lo = ws.who_lo; op.CoutP = ChP;
-      ge.mode = 2; ge.ugate = g_t; ge.u_s1 = g_bs; ge.out2 = h + (int64_t)t * h_ts; ge.o2_s1 = h_bs;
-      ge.pl_hi = ws.hpl_hi[sn]; ge.pl_lo = ws.hpl_lo[sn];
-      DVD_TRY(conv_fwd_ex(&d_o, nullptr, nullptr, g_t + 2 * chw, &op, &ge, st));
-      have_planes = true;
-      continue;
+    for (int sl = 0; sl < ns; ++sl) {      // step t of every chain, interleaved so that all chains have work queued
+      cudaStream_t ss = fk.stream(sl);
+      const int b0 = sl * Bn;
+      const float* hp = first ? nullptr : (t > 0 ? h + (int64_t)(t - 1) * h_ts : h0) + (int64_t)b0 * hp_bs;
+      float* g_t = gates + (int64_t)t * g_ts + (int64_t)b0 * g_bs;
+      float* rh_t = rh + (int64_t)t * h_ts + (int64_t)b0 * h_bs;
+      float* h_t = h + (int64_t)t * h_ts + (int64_t)b0 * h_bs;
+      if (fused && hp) {
+        const int sp = (t + 1) & 1, sn = t & 1;          // slots of h_{t-1} and h_t
+        const size_t po = (size_t)b0 * HW * ChP;         // this slice's rows of the [B*HW][ChP] planes
+        if (!have_planes)
+          DVD_TRY(tma_split_activations(hp, Bn, Ch, hp_bs, HW, HW, f16, ws.hpl_hi[sp] + po, ws.hpl_lo[sp] + po, ss));
+        TmaOperands op;
+        GruEpi ge;
+        op.a_hi = ws.hpl_hi[sp] + po; op.a_lo = ws.hpl_lo[sp] + po; op.w_hi = ws.whur_hi; op.w_lo = ws.whur_lo;
+        op.CoutP = Co2P;
+        ge.mode = 1; ge.Ch = Ch; ge.hprev = hp; ge.hp_s1 = hp_bs; ge.out2 = rh_t; ge.o2_s1 = h_bs;
+        ge.pl_hi = ws.rhpl_hi + po; ge.pl_lo = ws.rhpl_lo + po; ge.pl_Cp = ChP;
+        DVD_TRY(conv_fwd_ex(&d_ur, nullptr, nullptr, g_t, &op, &ge, ss));
+        op.a_hi = ws.rhpl_hi + po; op.a_lo = ws.rhpl_lo + po; op.w_hi = ws.who_hi; op.w_lo = ws.who_lo; op.CoutP = ChP;
+        ge.mode = 2; ge.ugate = g_t; ge.u_s1 = g_bs; ge.out2 = h_t; ge.o2_s1 = h_bs;
+        ge.pl_hi = ws.hpl_hi[sn] + po; ge.pl_lo = ws.hpl_lo[sn] + po;
+        DVD_TRY(conv_fwd_ex(&d_o, nullptr, nullptr, g_t + 2 * chw, &op, &ge, ss));
+        continue;
+      }
+      if (hp) {
+        dvd_conv_desc d = base_desc(Bn, 1, Ch, 2 * Ch, H, W, k); d.x_kind = 1;
+        d.x_s1 = hp_bs; d.y_s1 = g_bs; d.accumulate = 1;
+        DVD_TRY(dvd_conv_fwd(&d, hp, ws.whur, nullptr, nullptr, g_t, ss));
+      }
+      { ProfScope ps(3, "gru_gate_ur", ss); gru_gate_ur_kernel<<<eb, 256, 0, ss>>>(g_t, g_bs, hp, hp_bs, rh_t, h_bs, Bn, chw); }
+      DVD_LAUNCH_CHECK();
+      if (hp) {
+        dvd_conv_desc d = base_desc(Bn, 1, Ch, Ch, H, W, k); d.x_kind = 1;
+        d.x_s1 = h_bs; d.y_s1 = g_bs; d.accumulate = 1;
+        DVD_TRY(dvd_conv_fwd(&d, rh_t, ws.who, nullptr, nullptr, g_t + 2 * chw, ss));
+      }
+      { ProfScope ps(3, "gru_out", ss); gru_out_kernel<<<eb, 256, 0, ss>>>(g_t, g_bs, hp, hp_bs, h_t, h_bs, Bn, chw); }
+      DVD_LAUNCH_CHECK();
     }
-    have_planes = false;
-    if (hp) {
-      dvd_conv_desc d = base_desc(B, 1, Ch, 2 * Ch, H, W, k); d.x_kind = 1;
-      d.x_s1 = hp_bs; d.y_s1 = g_bs; d.accumulate = 1;
-      DVD_TRY(dvd_conv_fwd(&d, hp, ws.whur, nullptr, nullptr, g_t, stream));
-    }
-    { ProfScope ps(3, "gru_gate_ur", st); gru_gate_ur_kernel<<<eb, 256, 0, st>>>(g_t, g_bs, hp, hp_bs, rh_t, h_bs, B, chw); }
-    DVD_LAUNCH_CHECK();
-    if (hp) {
-      dvd_conv_desc d = base_desc(B, 1, Ch, Ch, H, W, k); d.x_kind = 1;
-      d.x_s1 = h_bs; d.y_s1 = g_bs; d.accumulate = 1;
-      DVD_TRY(dvd_conv_fwd(&d, rh_t, ws.who, nullptr, nullptr, g_t + 2 * chw, stream));
-    }
-    { ProfScope ps(3, "gru_out", st); gru_out_kernel<<<eb, 256, 0, st>>>(g_t, g_bs, hp, hp_bs, h + (int64_t)t * h_ts, h_bs, B, chw); }
-    DVD_LAUNCH_CHECK();
+    have_planes = fused && !first;
   }
+  DVD_TRY(fk.end());
   return 0;
 }
 
-extern "C" int dvd_convgru_layer_bwd(const float* x, int64_t x_bs, int64_t x_ts, const float* h0, const float* wu,
-                                     const float* wr, const float* wo, float* gates, const float* h, const float* rh,
-                                     const float* dh, float* dx, float* dh0, float* dwu, float* dwr, float* dwo,
-                                     float* dbu, float* dbr, float* dbo, int B, int T, int Cx, int Ch, int H, int W,
-                                     int k, void* workspace, size_t ws_bytes, void* stream) {
+extern "C" int dvd_convgru_layer_fwd(const float* x, int64_t x_bs, int64_t x_ts, const float* h0, const float* wu,
+                                     const float* wr, const float* wo, const float* bu, const float* br,
+                                     const float* bo, float* gates, float* h, float* rh, int B, int T, int Cx, int Ch,
+                                     int H, int W, int k, void* workspace, size_t ws_bytes, void* stream) {
+  return gru_fwd_impl(x, x_bs, x_ts, h0, wu, wr, wo, bu, br, bo, gates, h, rh, B, T, Cx, Ch, H, W, k, 0, T, false,
+                      workspace, ws_bytes, stream);
+}
+
+extern "C" int dvd_convgru_layer_fwd_range(const float* x, int64_t x_bs, int64_t x_ts, const float* h0, const float* wu,
+                                           const float* wr, const float* wo, const float* bu, const float* br,
+                                           const float* bo, float* gates, float* h, float* rh, int B, int T, int Cx,
+                                           int Ch, int H, int W, int k, int t0, int t1, void* workspace, size_t ws_bytes,
+                                           void* stream) {
+  return gru_fwd_impl(x, x_bs, x_ts, h0, wu, wr, wo, bu, br, bo, gates, h, rh, B, T, Cx, Ch, H, W, k, t0, t1, true,
+                      workspace, ws_bytes, stream);
+}
+
+// Frames [t0, t1) of the BPTT sweep, latest frame first.  range = false: the whole clip in one call.  range = true: one
+// of several calls that share `workspace` (dvd_convgru_layer_range_workspace_bytes) and visit the frames in descending
+// order: the call with t1 = T prepares the weights, every call leaves dx of its frames, the call with t0 = 0 finishes
+// with dh0, the weight and bias gradients.
+static int gru_bwd_impl(const float* x, int64_t x_bs, int64_t x_ts, const float* h0, const float* wu, const float* wr,
+                        const float* wo, float* gates, const float* h, const float* rh, const float* dh, float* dx,
+                        float* dh0, float* dwu, float* dwr, float* dwo, float* dbu, float* dbr, float* dbo, int B, int T,
+                        int Cx, int Ch, int H, int W, int k, int t0, int t1, bool range, void* workspace,
+                        size_t ws_bytes, void* stream) {
   DVD_CHECK_ARG(x && wu && wr && wo && gates && h && rh && dh && dx && dwu && dwr && dwo && dbu && dbr && dbo);
   DVD_CHECK_ARG(workspace && B > 0 && T > 0 && Cx > 0 && Ch > 0 && H > 0 && W > 0 && (k & 1));
   DVD_CHECK_ARG(dh0 == nullptr || h0 != nullptr);
+  DVD_CHECK_ARG(0 <= t0 && t0 < t1 && t1 <= T);
   const int HW = H * W, taps = k * k, Ct = Cx + Ch;
-  GruWs ws = carve(workspace, B, Cx, Ch, HW, taps, true);
+  GruWs ws = carve(workspace, B, Cx, Ch, HW, taps, true, range ? T : 0);
   DVD_CHECK_ARG(ws.bytes <= ws_bytes);
   cudaStream_t st = as_stream(stream);
+  const bool begin = t1 == T, finish = t0 == 0;
   const float* wsrc[3] = {wu, wr, wo};
   float* dwdst[3] = {dwu, dwr, dwo};
   float* dbdst[3] = {dbu, dbr, dbo};
   // dgrad operands (transposed + flipped): [tap'][gate rows (u|r|o)][ci]
-  for (int g = 0; g < 3; ++g) {
+  for (int g = 0; g < 3 && begin; ++g) {
     DVD_TRY(dvd_weight_pack(wsrc[g], Ct, taps, 0, Ch, 0, Cx, nullptr, 1, ws.wxT, 3 * Ch, g * Ch, Cx, 0, stream));
     if (g < 2) DVD_TRY(dvd_weight_pack(wsrc[g], Ct, taps, 0, Ch, Cx, Ch, nullptr, 1, ws.whurT, 2 * Ch, g * Ch, Ch, 0, stream));
     else DVD_TRY(dvd_weight_pack(wsrc[g], Ct, taps, 0, Ch, Cx, Ch, nullptr, 1, ws.whoT, Ch, 0, Ch, 0, stream));
   }
   const int64_t chw = (int64_t)Ch * HW;
   const int64_t g_ts = 3 * chw, g_bs = (int64_t)T * g_ts, h_ts = chw, h_bs = (int64_t)T * chw;
-  const int eb = ew_blocks((int64_t)B * chw);
-  float* carry_in = nullptr;
-  float* carry_out = ws.carry0;
   // the two dgrad GEMMs of a step read the same transposed weights every step: split them into planes once
-  dvd_conv_desc d_rh = base_desc(B, 1, Ch, Ch, H, W, k), d_hp = base_desc(B, 1, 2 * Ch, Ch, H, W, k);
-  d_rh.x_s1 = d_hp.x_s1 = g_bs; d_rh.y_s1 = d_hp.y_s1 = chw; d_hp.accumulate = 1;
+  auto step_descs = [&](int Bn, dvd_conv_desc* rhd, dvd_conv_desc* hpd) {
+    *rhd = base_desc(Bn, 1, Ch, Ch, H, W, k); *hpd = base_desc(Bn, 1, 2 * Ch, Ch, H, W, k);
+    rhd->x_s1 = hpd->x_s1 = g_bs; rhd->y_s1 = hpd->y_s1 = chw; hpd->accumulate = 1;
+  };
+  dvd_conv_desc d_rh, d_hp;
+  const bool can_planes = gru_fused_enabled() && T > 1;
+  // chains over batch slices (see SliceFork); a caller of the frame-range API overlaps whole layers instead
+  const int ns = range ? 1 : pick_slices(B, T, [&](int Bn) {
+    step_descs(Bn, &d_rh, &d_hp);
+    return can_planes && conv_fwd_ex_eligible(&d_rh) && conv_fwd_ex_eligible(&d_hp);
+  });
+  const int Bn = B / ns;
+  step_descs(Bn, &d_rh, &d_hp);
+  const int eb = ew_blocks((int64_t)Bn * chw);
   const int ChP = tma_round64(Ch), Co2P = tma_round64(2 * Ch);
-  const bool wplanes = gru_fused_enabled() && T > 1 && conv_fwd_ex_eligible(&d_rh) && conv_fwd_ex_eligible(&d_hp);
-  if (wplanes) {
+  const bool wplanes = can_planes && conv_fwd_ex_eligible(&d_rh) && conv_fwd_ex_eligible(&d_hp);
+  if (wplanes && begin) {
     DVD_TRY(tma_split_weights(ws.whoT, taps, Ch, Ch, ChP, 0, ws.whoT_hi, ws.whoT_lo, st));
     DVD_TRY(tma_split_weights(ws.whurT, taps, 2 * Ch, Ch, ChP, 0, ws.whurT_hi, ws.whurT_lo, st));
   }
@@ -431,10 +569,14 @@ extern "C" int dvd_convgru_layer_bwd(const float* x, int64_t x_bs, int64_t x_ts,
   const int64_t pl_frame = (int64_t)HW * G3P, pl_img = (int64_t)T * pl_frame;
   if (share) {
     const size_t elems = (size_t)B * T * HW * G3P;
-    DVD_TRY(tma_scratch_alloc(&gp.p, 2 * elems * sizeof(uint16_t) + 256, st));
-    yo.y_hi = gp.p;
-    yo.y_lo = reinterpret_cast<uint16_t*>(gp.p) + elems;
-    pl_hi = reinterpret_cast<__nv_bfloat16*>(gp.p);
+    void* base = ws.gplanes;          // frame-range calls: the planes live in the workspace from call to call
+    if (!range) {
+      DVD_TRY(tma_scratch_alloc(&gp.p, 2 * elems * sizeof(uint16_t) + 256, st));
+      base = gp.p;
+    }
+    yo.y_hi = base;
+    yo.y_lo = reinterpret_cast<uint16_t*>(base) + elems;
+    pl_hi = reinterpret_cast<__nv_bfloat16*>(base);
     pl_lo = pl_hi + elems;
   }
   // Fused BPTT (option "gru_bwd_fused", off by default): the gate-gradient math between the two dgrad GEMMs of a step,
@@ -443,105 +585,129 @@ extern "C" int dvd_convgru_layer_bwd(const float* x, int64_t x_bs, int64_t x_ts,
   // their split-K dgrads).  Measured on config 2 (profiles/r2): helpers 135 -> 102 ms, fwd/dgrad GEMMs 1026 -> 1066 ms,
   // step unchanged -- with one accumulator set per CTA pair the tensor pipe waits for the longer epilogue.
   const bool bptt_fused = gplanes && get_option(OPT_GRU_BWD_FUSED) &&
-                          (int64_t)ceil_div(B * HW, 128) * ceil_div(Ch, 128) >= num_sms();
-  bool need_k1 = true;        // the elementwise part 1 of this step has not been done by the previous step's epilogue
-  for (int t = T - 1; t >= 0; --t) {
-    const float* hp = t > 0 ? h + (int64_t)(t - 1) * h_ts : h0;
+                          (int64_t)ceil_div(Bn * HW, 128) * ceil_div(Ch, 128) >= num_sms();
+  SliceFork fk(st, ns);
+  DVD_TRY(fk.begin());
+  // carry buffers ping-pong with the step: step t writes carry[(T-1-t) & 1] and reads the other one
+  float* const carry_buf[2] = {ws.carry0, ws.carry1};
+  // the elementwise part 1 of a step has not been done by the previous step's epilogue (mode 4).  The last step of a
+  // call never runs mode 4: it would read dh of frame t0 - 1, which a frame-range caller has not produced yet.
+  bool need_k1 = true;
+  for (int t = t1 - 1; t >= t0; --t) {
+    const bool first = t == 0 && !h0;
     const int64_t hp_bs = t > 0 ? h_bs : chw;
-    float* g_t = gates + (int64_t)t * g_ts;
-    float* carry_next = (carry_out == ws.carry0) ? ws.carry1 : ws.carry0;
-    const dim3 pgrid(ceil_div(HW, 32), Ch / 64, B);
-    if (need_k1) {
-      if (gplanes) {
-        ProfScope ps(3, "gru_bwd1", st);
-        gru_bwd1_planes_kernel<<<pgrid, 256, 0, st>>>(g_t, g_bs, hp, hp_bs, dh + (int64_t)t * h_ts, h_bs, carry_in,
-                                                       carry_out, Ch, HW, pl_hi + t * pl_frame, pl_lo + t * pl_frame,
-                                                       pl_img, G3P);
-      } else {
-        ProfScope ps(3, "gru_bwd1", st);
-        gru_bwd1_kernel<<<eb, 256, 0, st>>>(g_t, g_bs, hp, hp_bs, dh + (int64_t)t * h_ts, h_bs, carry_in, carry_out, B, chw);
-      }
-      DVD_LAUNCH_CHECK();
-    }
-    need_k1 = true;
-    if (hp && bptt_fused) {
-      // d(rh) = conv_o^T(da_o) with the reset-gate gradient in the epilogue (mode 3)
-      TmaOperands op;
-      op.w_hi = ws.whoT_hi; op.w_lo = ws.whoT_lo; op.CoutP = ChP;
-      op.a_hi = pl_hi + t * pl_frame; op.a_lo = pl_lo + t * pl_frame;
-      op.a_Cp = G3P; op.a_c_off = 2 * Ch; op.a_img_stride = pl_img;
-      GruEpi ge;
-      ge.mode = 3; ge.Ch = Ch; ge.hprev = hp; ge.hp_s1 = hp_bs; ge.ugate = g_t; ge.u_s1 = g_bs;
-      ge.out2 = carry_out; ge.o2_s1 = chw;
-      ge.pl_hi = pl_hi + t * pl_frame; ge.pl_lo = pl_lo + t * pl_frame; ge.pl_Cp = G3P; ge.pl_img = pl_img;
-      DVD_TRY(conv_fwd_ex(&d_rh, g_t + 2 * chw, ws.whoT, carry_out, &op, &ge, st));
-      // dh_{t-1} += conv_ur^T(da_u | da_r); for t > 0 the epilogue (mode 4) goes straight on with step t-1's part 1
-      op.w_hi = ws.whurT_hi; op.w_lo = ws.whurT_lo; op.a_c_off = 0;
-      if (t > 0) {
-        dvd_conv_desc d4 = d_hp;
-        d4.accumulate = 0;
-        GruEpi g4;
-        g4.mode = 4; g4.Ch = Ch; g4.ugate = gates + (int64_t)(t - 1) * g_ts; g4.u_s1 = g_bs;
-        g4.hprev = t > 1 ? h + (int64_t)(t - 2) * h_ts : h0; g4.hp_s1 = t > 1 ? h_bs : chw;
-        g4.carry_in = carry_out; g4.out2 = carry_next; g4.o2_s1 = chw;
-        g4.dh_prev = dh + (int64_t)(t - 1) * h_ts; g4.dh_s1 = h_bs;
-        g4.pl_hi = pl_hi + (t - 1) * pl_frame; g4.pl_lo = pl_lo + (t - 1) * pl_frame; g4.pl_Cp = G3P; g4.pl_img = pl_img;
-        DVD_TRY(conv_fwd_ex(&d4, g_t, ws.whurT, carry_next, &op, &g4, st));
-        need_k1 = false;
-      } else {
-        DVD_TRY(conv_fwd_ex(&d_hp, g_t, ws.whurT, carry_out, &op, nullptr, st));
-      }
-    } else {
-      if (hp) {                                                 // d(rh) = conv_o^T(da_o), h-half
-        if (wplanes) {
-          TmaOperands op;
-          op.w_hi = ws.whoT_hi; op.w_lo = ws.whoT_lo; op.CoutP = ChP;
-          if (gplanes) {
-            op.a_hi = pl_hi + t * pl_frame; op.a_lo = pl_lo + t * pl_frame;
-            op.a_Cp = G3P; op.a_c_off = 2 * Ch; op.a_img_stride = pl_img;
-          }
-          DVD_TRY(conv_fwd_ex(&d_rh, g_t + 2 * chw, ws.whoT, ws.d_rh, &op, nullptr, st));
+    const dim3 pgrid(ceil_div(HW, 32), Ch / 64, Bn);
+    bool did_k1_next = false;
+    for (int sl = 0; sl < ns; ++sl) {      // step t of every chain, interleaved
+      cudaStream_t ss = fk.stream(sl);
+      const int b0 = sl * Bn;
+      const int64_t co = (int64_t)b0 * chw;                       // this slice's rows of the (B, Ch*HW) buffers
+      const float* hp = first ? nullptr : (t > 0 ? h + (int64_t)(t - 1) * h_ts : h0) + (int64_t)b0 * hp_bs;
+      float* g_t = gates + (int64_t)t * g_ts + (int64_t)b0 * g_bs;
+      const float* dh_t = dh + (int64_t)t * h_ts + (int64_t)b0 * h_bs;
+      float* carry_out = carry_buf[(T - 1 - t) & 1] + co;
+      float* carry_next = carry_buf[(T - t) & 1] + co;
+      const float* carry_in = t == T - 1 ? nullptr : carry_next;
+      float* d_rh_s = ws.d_rh + co;
+      __nv_bfloat16* p_hi = pl_hi ? pl_hi + t * pl_frame + (int64_t)b0 * pl_img : nullptr;
+      __nv_bfloat16* p_lo = pl_lo ? pl_lo + t * pl_frame + (int64_t)b0 * pl_img : nullptr;
+      if (need_k1) {
+        if (gplanes) {
+          ProfScope ps(3, "gru_bwd1", ss);
+          gru_bwd1_planes_kernel<<<pgrid, 256, 0, ss>>>(g_t, g_bs, hp, hp_bs, dh_t, h_bs, carry_in, carry_out, Ch, HW,
+                                                         p_hi, p_lo, pl_img, G3P);
         } else {
-          DVD_TRY(dvd_conv_fwd(&d_rh, g_t + 2 * chw, ws.whoT, nullptr, nullptr, ws.d_rh, stream));
+          ProfScope ps(3, "gru_bwd1", ss);
+          gru_bwd1_kernel<<<eb, 256, 0, ss>>>(g_t, g_bs, hp, hp_bs, dh_t, h_bs, carry_in, carry_out, Bn, chw);
+        }
+        DVD_LAUNCH_CHECK();
+      }
+      if (hp && bptt_fused) {
+        // d(rh) = conv_o^T(da_o) with the reset-gate gradient in the epilogue (mode 3)
+        TmaOperands op;
+        op.w_hi = ws.whoT_hi; op.w_lo = ws.whoT_lo; op.CoutP = ChP;
+        op.a_hi = p_hi; op.a_lo = p_lo;
+        op.a_Cp = G3P; op.a_c_off = 2 * Ch; op.a_img_stride = pl_img;
+        GruEpi ge;
+        ge.mode = 3; ge.Ch = Ch; ge.hprev = hp; ge.hp_s1 = hp_bs; ge.ugate = g_t; ge.u_s1 = g_bs;
+        ge.out2 = carry_out; ge.o2_s1 = chw;
+        ge.pl_hi = p_hi; ge.pl_lo = p_lo; ge.pl_Cp = G3P; ge.pl_img = pl_img;
+        DVD_TRY(conv_fwd_ex(&d_rh, g_t + 2 * chw, ws.whoT, carry_out, &op, &ge, ss));
+        // dh_{t-1} += conv_ur^T(da_u | da_r); up to the last step of the call the epilogue (mode 4) goes straight on with
+        // step t-1's part 1
+        op.w_hi = ws.whurT_hi; op.w_lo = ws.whurT_lo; op.a_c_off = 0;
+        if (t > t0) {
+          dvd_conv_desc d4 = d_hp;
+          d4.accumulate = 0;
+          GruEpi g4;
+          g4.mode = 4; g4.Ch = Ch; g4.ugate = g_t - g_ts; g4.u_s1 = g_bs;
+          g4.hprev = t > 1 ? h + (int64_t)(t - 2) * h_ts + (int64_t)b0 * h_bs : (h0 ? h0 + (int64_t)b0 * chw : nullptr);
+          g4.hp_s1 = t > 1 ? h_bs : chw;
+          g4.carry_in = carry_out; g4.out2 = carry_next; g4.o2_s1 = chw;
+          g4.dh_prev = dh_t - h_ts; g4.dh_s1 = h_bs;
+          g4.pl_hi = p_hi - pl_frame; g4.pl_lo = p_lo - pl_frame; g4.pl_Cp = G3P; g4.pl_img = pl_img;
+          DVD_TRY(conv_fwd_ex(&d4, g_t, ws.whurT, carry_next, &op, &g4, ss));
+          did_k1_next = true;
+        } else {
+          DVD_TRY(conv_fwd_ex(&d_hp, g_t, ws.whurT, carry_out, &op, nullptr, ss));
+        }
+      } else {
+        if (hp) {                                                 // d(rh) = conv_o^T(da_o), h-half
+          if (wplanes) {
+            TmaOperands op;
+            op.w_hi = ws.whoT_hi; op.w_lo = ws.whoT_lo; op.CoutP = ChP;
+            if (gplanes) {
+              op.a_hi = p_hi; op.a_lo = p_lo;
+              op.a_Cp = G3P; op.a_c_off = 2 * Ch; op.a_img_stride = pl_img;
+            }
+            DVD_TRY(conv_fwd_ex(&d_rh, g_t + 2 * chw, ws.whoT, d_rh_s, &op, nullptr, ss));
+          } else {
+            DVD_TRY(dvd_conv_fwd(&d_rh, g_t + 2 * chw, ws.whoT, nullptr, nullptr, d_rh_s, ss));
+          }
+        }
+        if (gplanes) {
+          ProfScope ps(3, "gru_bwd2", ss);
+          gru_bwd2_planes_kernel<<<pgrid, 256, 0, ss>>>(g_t, g_bs, hp, hp_bs, d_rh_s, carry_out, Ch, HW, p_hi, p_lo,
+                                                         pl_img, G3P);
+        } else {
+          ProfScope ps(3, "gru_bwd2", ss);
+          gru_bwd2_kernel<<<eb, 256, 0, ss>>>(g_t, g_bs, hp, hp_bs, d_rh_s, carry_out, Bn, chw);
+        }
+        DVD_LAUNCH_CHECK();
+        if (hp) {                                                 // dh_prev += conv_u^T(da_u) + conv_r^T(da_r)
+          if (wplanes) {
+            TmaOperands op;
+            op.w_hi = ws.whurT_hi; op.w_lo = ws.whurT_lo; op.CoutP = ChP;
+            if (gplanes) {
+              op.a_hi = p_hi; op.a_lo = p_lo;
+              op.a_Cp = G3P; op.a_c_off = 0; op.a_img_stride = pl_img;
+            }
+            DVD_TRY(conv_fwd_ex(&d_hp, g_t, ws.whurT, carry_out, &op, nullptr, ss));
+          } else {
+            DVD_TRY(dvd_conv_fwd(&d_hp, g_t, ws.whurT, nullptr, nullptr, carry_out, ss));
+          }
         }
       }
-      if (gplanes) {
-        ProfScope ps(3, "gru_bwd2", st);
-        gru_bwd2_planes_kernel<<<pgrid, 256, 0, st>>>(g_t, g_bs, hp, hp_bs, ws.d_rh, carry_out, Ch, HW,
-                                                       pl_hi + t * pl_frame, pl_lo + t * pl_frame, pl_img, G3P);
-      } else {
-        ProfScope ps(3, "gru_bwd2", st);
-        gru_bwd2_kernel<<<eb, 256, 0, st>>>(g_t, g_bs, hp, hp_bs, ws.d_rh, carry_out, B, chw);
-      }
-      DVD_LAUNCH_CHECK();
-      if (hp) {                                                 // dh_prev += conv_u^T(da_u) + conv_r^T(da_r)
-        if (wplanes) {
-          TmaOperands op;
-          op.w_hi = ws.whurT_hi; op.w_lo = ws.whurT_lo; op.CoutP = ChP;
-          if (gplanes) {
-            op.a_hi = pl_hi + t * pl_frame; op.a_lo = pl_lo + t * pl_frame;
-            op.a_Cp = G3P; op.a_c_off = 0; op.a_img_stride = pl_img;
-          }
-          DVD_TRY(conv_fwd_ex(&d_hp, g_t, ws.whurT, carry_out, &op, nullptr, st));
-        } else {
-          DVD_TRY(dvd_conv_fwd(&d_hp, g_t, ws.whurT, nullptr, nullptr, carry_out, stream));
-        }
-      }
     }
-    carry_in = carry_out;
-    carry_out = carry_next;
+    need_k1 = !did_k1_next;
   }
-  if (dh0) DVD_CUDA(cudaMemcpyAsync(dh0, carry_in, sizeof(float) * (size_t)B * chw, cudaMemcpyDeviceToDevice, st));
-  if (share && !gplanes)
+  DVD_TRY(fk.end());
+  const float* carry_in = carry_buf[(T - 1) & 1];          // what step 0 wrote: dL/dh_{-1}
+  if (dh0 && finish) DVD_CUDA(cudaMemcpyAsync(dh0, carry_in, sizeof(float) * (size_t)B * chw, cudaMemcpyDeviceToDevice, st));
+  if (share && !gplanes && finish)
     DVD_TRY(tma_split_gradients(gates, B * T, 3 * Ch, g_ts, HW, HW, const_cast<void*>(yo.y_hi), const_cast<void*>(yo.y_lo), st));
-  // dx for all frames: one implicit GEMM over the (da_u | da_r | da_o) buffer
-  if (share) {
+  // dx of the frames of this call: one implicit GEMM over the (da_u | da_r | da_o) buffer
+  if (share && begin && finish) {
     TmaOperands op;
     op.a_hi = yo.y_hi; op.a_lo = yo.y_lo;
     DVD_TRY(conv_fwd_ex(&d_dx, gates, ws.wxT, dx, &op, nullptr, st));
   } else {
-    DVD_TRY(dvd_conv_fwd(&d_dx, gates, ws.wxT, nullptr, nullptr, dx, stream));
+    // (a frame range of the [B][T] planes is not one strided run of images: this GEMM splits its operand itself)
+    dvd_conv_desc d = d_dx;
+    d.N2 = t1 - t0;
+    DVD_TRY(dvd_conv_fwd(&d, gates + (int64_t)t0 * g_ts, ws.wxT, nullptr, nullptr, dx + (int64_t)t0 * d_dx.y_s2, stream));
   }
+  if (!finish) return 0;
   // weight gradients, batched over time
   if (share) {
     yo.y_c_off = 0; yo.y_t_off = 0;
@@ -585,4 +751,23 @@ extern "C" int dvd_convgru_layer_bwd(const float* x, int64_t x_bs, int64_t x_ts,
   for (int g = 0; g < 3; ++g)
     DVD_CUDA(cudaMemcpyAsync(dbdst[g], ws.dbias + g * Ch, sizeof(float) * Ch, cudaMemcpyDeviceToDevice, st));
   return 0;
+}
+
+extern "C" int dvd_convgru_layer_bwd(const float* x, int64_t x_bs, int64_t x_ts, const float* h0, const float* wu,
+                                     const float* wr, const float* wo, float* gates, const float* h, const float* rh,
+                                     const float* dh, float* dx, float* dh0, float* dwu, float* dwr, float* dwo,
+                                     float* dbu, float* dbr, float* dbo, int B, int T, int Cx, int Ch, int H, int W,
+                                     int k, void* workspace, size_t ws_bytes, void* stream) {
+  return gru_bwd_impl(x, x_bs, x_ts, h0, wu, wr, wo, gates, h, rh, dh, dx, dh0, dwu, dwr, dwo, dbu, dbr, dbo, B, T, Cx,
+                      Ch, H, W, k, 0, T, false, workspace, ws_bytes, stream);
+}
+
+extern "C" int dvd_convgru_layer_bwd_range(const float* x, int64_t x_bs, int64_t x_ts, const float* h0, const float* wu,
+                                           const float* wr, const float* wo, float* gates, const float* h,
+                                           const float* rh, const float* dh, float* dx, float* dh0, float* dwu,
+                                           float* dwr, float* dwo, float* dbu, float* dbr, float* dbo, int B, int T,
+                                           int Cx, int Ch, int H, int W, int k, int t0, int t1, void* workspace,
+                                           size_t ws_bytes, void* stream) {
+  return gru_bwd_impl(x, x_bs, x_ts, h0, wu, wr, wo, gates, h, rh, dh, dx, dh0, dwu, dwr, dwo, dbu, dbr, dbo, B, T, Cx,
+                      Ch, H, W, k, t0, t1, true, workspace, ws_bytes, stream);
 }

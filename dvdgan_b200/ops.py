@@ -5,6 +5,7 @@ PyTorch supplies device memory (``torch.empty``), streams and the autograd tape.
 ATen fallback: a missing library or a CPU tensor raises.
 """
 import ctypes
+import os
 
 import torch
 
@@ -552,6 +553,158 @@ class GRULayerFn(torch.autograd.Function):
             call("dvd_bgemm", 0, 0, 1, n, T, 1.0, ptr(ones), T, 0, ptr(dx), n, T * n, 0.0, ptr(dxs), n, n, B, None)
             dx = dxs
         return dx, dh0, dwu, dwr, dwo, dbu, dbr, dbo, None
+
+
+# ---- the layers of a ConvGRU stack as a wavefront (Generator.py:87-97: layer l+1 of frame t needs layer l of frame t only)
+# GRULayerFn runs one layer over the whole clip before the next layer starts: a chain of 2T dependent GEMM launches that,
+# on the small stages (4x4 / 8x8 / 16x16 frames, or few clips per GPU), are latency-bound -- a 200-k-block reduction on a
+# handful of row tiles takes ~130 us however few rows there are, and most SMs idle.  GRUStackFn cuts the clip into chunks
+# of frames and runs layer l on stream l: layer l works on chunk c while layer l-1 is already on chunk c+1, so up to
+# n_layers independent chains are in flight (forward and BPTT).  Same kernels, same operands, same results.
+# max_rows: only stages with at most this many output pixels per time step (B*H*W) -- above it one layer's GEMMs fill the
+# machine for several waves, the batch chains of the library (option "gru_streams") fill the tails equally well
+# (measured, profiles/r2) and the wavefront's extra transient memory (three layers' gradient planes at once) buys nothing
+GRU_WAVEFRONT = {"enabled": 1, "chunk": 8, "max_rows": 32768}
+for _kv in filter(None, os.environ.get("DVD_GRU_WAVEFRONT", "").split(",")):        # A/B runs: "enabled=0", "chunk=4"
+    _k, _, _v = _kv.partition("=")
+    GRU_WAVEFRONT[_k.strip()] = int(_v)
+_WAVE_STREAMS = {}
+
+
+def _wave_streams(dev, n):
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    pool = _WAVE_STREAMS.setdefault(key, [])
+    while len(pool) < n:
+        pool.append(torch.cuda.Stream(device=dev))
+    return pool[:n]
+
+
+def _is_lean(sig):
+    return GRU_LEAN is True or (GRU_LEAN is not False and sig in GRU_LEAN)
+
+
+def gru_wavefront_chunk(B, T, sigs):
+    """Frames per chunk for a stack of layers with signatures (Cx, Ch, H, W, k), or 0 when the stack runs layer by
+    layer: one layer, one frame, a layer in lean mode (its recomputation is per layer), or a stage above ``max_rows``."""
+    w = GRU_WAVEFRONT
+    if not w["enabled"] or len(sigs) < 2 or T < 2 or any(_is_lean(sg) for sg in sigs):
+        return 0
+    if w["max_rows"] and B * sigs[0][2] * sigs[0][3] > w["max_rows"]:
+        return 0
+    return max(1, min(int(w["chunk"]), (T + 2) // 3))
+
+
+class GRUStackFn(torch.autograd.Function):
+    """ConvGRU.forward_sequence for a stack of layers with zero initial state: h of the LAST layer for every frame.
+    apply(x, T_bcast, chunk, wu0, wr0, wo0, bu0, br0, bo0, wu1, ...)."""
+
+    @staticmethod
+    def _bounds(T, chunk):
+        return [(t0, min(t0 + chunk, T)) for t0 in range(0, T, chunk)]
+
+    @staticmethod
+    def forward(ctx, x, T_bcast, chunk, *params):
+        _C.require_cuda(x, *params)
+        x = _c(x)
+        if T_bcast:
+            B, Cx, H, W = x.shape
+            T = T_bcast
+            x_bs, x_ts = Cx * H * W, 0
+        else:
+            B, T, Cx, H, W = x.shape
+            x_bs, x_ts = T * Cx * H * W, Cx * H * W
+        L = len(params) // 6
+        lib = _C.lib()
+        layers, inp = [], x
+        for l in range(L):
+            wu = params[6 * l]
+            Ch, k = wu.shape[0], wu.shape[-1]
+            nbytes = lib.dvd_convgru_layer_workspace_bytes(B, T, Cx, Ch, H, W, k)
+            layers.append(dict(x=inp, x_bs=x_bs, x_ts=x_ts, Cx=Cx, Ch=Ch, k=k, gates=_new((B, T, 3 * Ch, H, W), x),
+                               h=_new((B, T, Ch, H, W), x), rh=_new((B, T, Ch, H, W), x), nbytes=nbytes,
+                               ws=torch.empty(nbytes, device=x.device, dtype=torch.uint8)))
+            inp, Cx, x_bs, x_ts = layers[-1]["h"], Ch, T * Ch * H * W, Ch * H * W
+        main = torch.cuda.current_stream(x.device)
+        streams = _wave_streams(x.device, L)
+        start = torch.cuda.Event()
+        start.record(main)
+        for st in streams:
+            st.wait_event(start)
+        prev = [None] * L          # event: layer l has finished the chunk being enqueued
+        for t0, t1 in GRUStackFn._bounds(T, chunk):
+            for l, ly in enumerate(layers):
+                w = params[6 * l:6 * l + 6]
+                with torch.cuda.stream(streams[l]):
+                    if l > 0:
+                        streams[l].wait_event(prev[l - 1])
+                    call("dvd_convgru_layer_fwd_range", ptr(ly["x"]), ly["x_bs"], ly["x_ts"], None, ptr(w[0]), ptr(w[1]),
+                         ptr(w[2]), ptr(w[3]), ptr(w[4]), ptr(w[5]), ptr(ly["gates"]), ptr(ly["h"]), ptr(ly["rh"]), B, T,
+                         ly["Cx"], ly["Ch"], H, W, ly["k"], t0, t1, ptr(ly["ws"]), ly["nbytes"])
+                    prev[l] = torch.cuda.Event()
+                    prev[l].record(streams[l])
+        for st in streams:          # the caller's stream continues after every layer (and only then are buffers released)
+            e = torch.cuda.Event()
+            e.record(st)
+            main.wait_event(e)
+        ctx.save_for_backward(x, *params, *[t for ly in layers for t in (ly["gates"], ly["h"], ly["rh"])])
+        ctx.cfg = (B, T, H, W, T_bcast, chunk, [(ly["Cx"], ly["Ch"], ly["k"], ly["x_bs"], ly["x_ts"]) for ly in layers])
+        ctx.consumed = False
+        return layers[-1]["h"]
+
+    @staticmethod
+    def backward(ctx, dh_last):
+        if ctx.consumed:
+            raise RuntimeError("GRUStackFn: second backward through the same graph -- the saved gate buffers were "
+                               "overwritten in place by the first one (the reference trainer backpropagates once)")
+        ctx.consumed = True
+        B, T, H, W, T_bcast, chunk, lcfg = ctx.cfg
+        L = len(lcfg)
+        saved = ctx.saved_tensors
+        x, params, states = saved[0], saved[1:1 + 6 * L], saved[1 + 6 * L:]
+        dh_last = _c(dh_last)
+        lib = _C.lib()
+        work = []
+        for l, (Cx, Ch, k, x_bs, x_ts) in enumerate(lcfg):
+            w = params[6 * l:6 * l + 6]
+            nbytes = lib.dvd_convgru_layer_range_workspace_bytes(B, T, Cx, Ch, H, W, k)
+            work.append(dict(dx=_new((B, T, Cx, H, W), x), dw=[_new(t.shape, x) for t in w], nbytes=nbytes,
+                             ws=torch.empty(nbytes, device=x.device, dtype=torch.uint8)))
+        main = torch.cuda.current_stream(x.device)
+        streams = _wave_streams(x.device, L)
+        start = torch.cuda.Event()
+        start.record(main)
+        for st in streams:
+            st.wait_event(start)
+        prev = [None] * L          # event: layer l has produced dx (= dh of layer l-1) of the chunk being enqueued
+        for t0, t1 in reversed(GRUStackFn._bounds(T, chunk)):
+            for l in reversed(range(L)):
+                Cx, Ch, k, x_bs, x_ts = lcfg[l]
+                w, wk = params[6 * l:6 * l + 6], work[l]
+                gates, h, rh = states[3 * l:3 * l + 3]
+                xin = x if l == 0 else states[3 * (l - 1) + 1]
+                dh = dh_last if l == L - 1 else work[l + 1]["dx"]
+                with torch.cuda.stream(streams[l]):
+                    if l < L - 1:
+                        streams[l].wait_event(prev[l + 1])
+                    # NB: overwrites `gates` in place with the pre-activation gradients
+                    call("dvd_convgru_layer_bwd_range", ptr(xin), x_bs, x_ts, None, ptr(w[0]), ptr(w[1]), ptr(w[2]),
+                         ptr(gates), ptr(h), ptr(rh), ptr(dh), ptr(wk["dx"]), None, *[ptr(t) for t in wk["dw"]], B, T,
+                         Cx, Ch, H, W, k, t0, t1, ptr(wk["ws"]), wk["nbytes"])
+                    prev[l] = torch.cuda.Event()
+                    prev[l].record(streams[l])
+        for st in streams:
+            e = torch.cuda.Event()
+            e.record(st)
+            main.wait_event(e)
+        dx = work[0]["dx"]
+        if T_bcast:          # sum over frames: dx_sum[b] = ones(1,T) @ dx[b] (T, Cx*H*W)
+            Cx = lcfg[0][0]
+            ones = torch.ones(T, device=x.device, dtype=F32)
+            dxs = _new((B, Cx, H, W), x)
+            n = Cx * H * W
+            call("dvd_bgemm", 0, 0, 1, n, T, 1.0, ptr(ones), T, 0, ptr(dx), n, T * n, 0.0, ptr(dxs), n, n, B, None)
+            dx = dxs
+        return (dx, None, None) + tuple(g for wk in work for g in wk["dw"])
 
 
 class AvgPoolFn(torch.autograd.Function):

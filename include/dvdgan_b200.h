@@ -140,6 +140,32 @@ int dvd_convgru_layer_bwd(const float* x, int64_t x_bs, int64_t x_ts, const floa
                           float* dbu, float* dbr, float* dbo,
                           int B, int T, int Cx, int Ch, int H, int W, int k,
                           void* workspace, size_t ws_bytes, void* stream);
+/* Both calls split the batch into `gru_streams` (option, default 2) independent chains over B / n clips: chain 0 runs
+ * on `stream`, the others on library-owned non-blocking helper streams (one set per host thread and device) that are
+ * forked from and joined to `stream` with events inside the call, so the call stays stream-ordered for its caller.
+ *
+ * The same sweeps over a RANGE of frames [t0, t1), for callers that overlap the layers of a ConvGRU stack
+ * (Generator.py:87-97 runs layer l+1 of frame t right after layer l: nothing forces a layer to finish its clip before
+ * the next one starts).  All tensor arguments are the whole-clip buffers of the calls above; a call touches frames
+ * [t0, t1) only.  Forward: calls that share `workspace` visit the frames in ascending order, the first one (t0 = 0)
+ * prepares the weights there.  Backward: calls that share `workspace` (dvd_convgru_layer_range_workspace_bytes: it
+ * also holds the gate-gradient operand planes of the whole clip) visit the frames in descending order starting at
+ * t1 = T; every call needs dh of its frames and leaves dx of its frames; the last one (t0 = 0) also writes dh0 and the
+ * weight / bias gradients.  No helper streams here: the caller supplies the concurrency (one stream per layer). */
+size_t dvd_convgru_layer_range_workspace_bytes(int B, int T, int Cx, int Ch, int H, int W, int k);
+int dvd_convgru_layer_fwd_range(const float* x, int64_t x_bs, int64_t x_ts, const float* h0,
+                                const float* wu, const float* wr, const float* wo,
+                                const float* bu, const float* br, const float* bo,
+                                float* gates, float* h, float* rh,
+                                int B, int T, int Cx, int Ch, int H, int W, int k, int t0, int t1,
+                                void* workspace, size_t ws_bytes, void* stream);
+int dvd_convgru_layer_bwd_range(const float* x, int64_t x_bs, int64_t x_ts, const float* h0,
+                                const float* wu, const float* wr, const float* wo,
+                                float* gates, const float* h, const float* rh, const float* dh,
+                                float* dx, float* dh0, float* dwu, float* dwr, float* dwo,
+                                float* dbu, float* dbr, float* dbo,
+                                int B, int T, int Cx, int Ch, int H, int W, int k, int t0, int t1,
+                                void* workspace, size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Normalisation

@@ -561,6 +561,92 @@ def test_fused_bptt_epilogues_match_separate_kernels(dev, with_h0):
         assert rel(a, b) < 2e-5, rel(a, b)
 
 
+@pytest.mark.parametrize("shape,with_h0,bwd_fused", [
+    ((8, 6, 64, 128, 16, 16, 3), False, 0),      # 4 chains of 2 clips (512 rows each)
+    ((8, 5, 128, 64, 32, 32, 5), True, 0),       # with an initial state
+    ((48, 4, 128, 128, 32, 32, 5), True, 1),     # persistent pair tiles, fused BPTT epilogues
+    ((6, 4, 64, 64, 8, 8, 3), False, 0),         # 4 does not divide the batch: falls back to 3 chains
+    ((3, 3, 64, 64, 4, 4, 3), False, 0),         # slices too small for the tensor path: one chain
+])
+def test_convgru_batch_slices_on_helper_streams(dev, shape, with_h0, bwd_fused):
+    """option "gru_streams": the time loops of a ConvGRU layer (forward sweep and BPTT) run as independent chains over
+    batch slices on library-owned helper streams, forked from / joined to the caller's stream.  The clips of a batch do
+    not interact inside a ConvGRU (ConvGRU.py:29-54), so every chain count gives the one-chain result (to the
+    summation-order noise of the split-K atomics), with work queued on the caller's stream before and after the call
+    ordered against the chains."""
+    from dvdgan_b200 import _C, ops
+    B, T, Cx, Ch, H, W, k = shape
+    torch.manual_seed(31)
+    x = torch.randn(B, T, Cx, H, W, device=dev) * 0.7
+    h0 = torch.randn(B, Ch, H, W, device=dev) * 0.3 if with_h0 else None
+    ws = [(torch.randn(Ch, Cx + Ch, k, k, device=dev) * 0.03).requires_grad_(True) for _ in range(3)]
+    bs = [(torch.randn(Ch, device=dev) * 0.1).requires_grad_(True) for _ in range(3)]
+    wgt = torch.randn(B, T, Ch, H, W, device=dev)
+    default = _C.get_option("gru_streams")
+    res = {}
+    _C.set_option("gru_bwd_fused", bwd_fused)
+    try:
+        for n in (1, 2, 4):
+            _C.set_option("gru_streams", n)
+            # produced on the caller's stream right before the call / consumed right after it: both orderings matter
+            xx = (x * 2.0 - x).requires_grad_(True)
+            hh = (h0 + 0.0).requires_grad_(True) if with_h0 else None
+            h = ops.GRULayerFn.apply(xx, hh, ws[0], ws[1], ws[2], bs[0], bs[1], bs[2], 0)
+            out = h * 1.0
+            (out * wgt).sum().backward()
+            res[n] = [out.detach().clone(), xx.grad.clone()] + ([hh.grad.clone()] if with_h0 else []) + \
+                     [w.grad.clone() for w in ws] + [b.grad.clone() for b in bs]
+            for t in ws + bs:
+                t.grad = None
+    finally:
+        _C.set_option("gru_streams", default)
+        _C.set_option("gru_bwd_fused", 0)
+    for n in (2, 4):
+        for i, (a, b) in enumerate(zip(res[n], res[1])):
+            assert rel(a, b) < 2e-5, (n, i, rel(a, b))
+
+
+@pytest.mark.parametrize("shape,hidden,ks,bcast,chunk,bwd_fused", [
+    ((4, 7, 64, 8, 8), [64, 128, 64], [3, 5, 3], False, 3, 0),        # chunks of 3, 3, 1 frames
+    ((2, 6, 64, 4, 4), [64, 128, 64], [3, 5, 3], True, 2, 0),         # stage 0: one input frame fed to every step (Q13)
+    ((48, 5, 128, 32, 32), [128, 128], [5, 3], False, 2, 1),          # persistent pair tiles, fused BPTT epilogues
+    ((2, 4, 32, 16, 16), [32, 64, 32], [3, 5, 5], False, 1, 0),       # Ch % 64 != 0: planes split after the sweep
+])
+def test_convgru_stack_wavefront_matches_layer_by_layer(dev, shape, hidden, ks, bcast, chunk, bwd_fused):
+    """ops.GRUStackFn: the layers of a ConvGRU stack on one stream each, layer l a chunk of frames behind layer l-1
+    (dvd_convgru_layer_{fwd,bwd}_range), against ConvGRU.forward_sequence layer by layer (one whole-clip call per
+    layer).  Same kernels on the same operands: equal to summation-order noise, forward and every gradient."""
+    from dvdgan_b200 import _C, ops
+    from dvdgan_b200.Module.ConvGRU import ConvGRU
+    B, T, Cx, H, W = shape
+    torch.manual_seed(41)
+    net = ConvGRU(Cx, hidden, ks, len(hidden)).to(dev)
+    with torch.no_grad():
+        for p in net.parameters():          # (orthogonal init / zero biases are a special case)
+            p.add_(torch.randn_like(p) * 0.01)
+    x = torch.randn(B, Cx, H, W, device=dev) if bcast else torch.randn(B, T, Cx, H, W, device=dev) * 0.7
+    wgt = torch.randn(B, T, hidden[-1], H, W, device=dev)
+    saved = dict(ops.GRU_WAVEFRONT)
+    res = {}
+    _C.set_option("gru_bwd_fused", bwd_fused)
+    try:
+        for wave in (0, 1):
+            ops.GRU_WAVEFRONT.update(enabled=wave, chunk=chunk, max_rows=0)
+            xx = (x * 2.0 - x).requires_grad_(True)          # produced on the caller's stream right before the call
+            h = net.forward_sequence(xx, T_bcast=T if bcast else 0)
+            assert (type(h.grad_fn).__name__ == "GRUStackFnBackward") == bool(wave)
+            out = h * 1.0
+            (out * wgt).sum().backward()
+            res[wave] = [out.detach().clone(), xx.grad.clone()] + [p.grad.clone() for p in net.parameters()]
+            net.zero_grad()
+    finally:
+        ops.GRU_WAVEFRONT.clear()
+        ops.GRU_WAVEFRONT.update(saved)
+        _C.set_option("gru_bwd_fused", 0)
+    for i, (a, b) in enumerate(zip(res[1], res[0])):
+        assert rel(a, b) < 2e-5, (i, rel(a, b))
+
+
 def test_generator_with_optional_attention_blocks(dev):
     """Generator(attention=True) wires in the two non-local blocks the reference leaves commented out
     (Generator.py:28-36).  Their gamma is initialised to 0 (Attention.py), so with the same weights the output is the

@@ -73,3 +73,25 @@ def test_fixture_sampler_is_deterministic():
     a, b = sample_idx("out", 10 ** 6, 1000), sample_idx("out", 10 ** 6, 1000)
     assert torch.equal(a, b) and a.max() < 10 ** 6 and not torch.equal(a, sample_idx("pre_tanh", 10 ** 6, 1000))
     assert torch.equal(sample_idx("x", 10, 1000), torch.arange(10))
+
+
+def test_convgru_stack_wavefront_policy():
+    """the wavefront needs every layer's full state: a lean layer (its gates are recomputed per layer) or a stage above
+    ``max_rows`` sends the stack down the layer-by-layer path."""
+    from dvdgan_b200 import ops
+    sigs = [(256, 256, 8, 8, 3), (256, 512, 8, 8, 5), (512, 256, 8, 8, 3)]
+    saved = dict(ops.GRU_WAVEFRONT)
+    try:
+        ops.GRU_WAVEFRONT.update(enabled=1, chunk=8, max_rows=0)
+        assert ops.gru_wavefront_chunk(64, 48, sigs) == 8
+        assert ops.gru_wavefront_chunk(64, 12, sigs) == 4 and ops.gru_wavefront_chunk(64, 1, sigs) == 0
+        assert ops.gru_wavefront_chunk(64, 48, sigs[:1]) == 0
+        ops.set_gru_lean({sigs[1]})
+        assert ops.gru_wavefront_chunk(64, 48, sigs) == 0
+        ops.set_gru_lean(False)
+        ops.GRU_WAVEFRONT.update(max_rows=1024)
+        assert ops.gru_wavefront_chunk(64, 48, sigs) == 0 and ops.gru_wavefront_chunk(16, 48, sigs) == 8
+    finally:
+        ops.set_gru_lean(False)
+        ops.GRU_WAVEFRONT.clear()
+        ops.GRU_WAVEFRONT.update(saved)
