@@ -5,6 +5,11 @@
 // (B,T,3Ch,H,W) buffer = (update, reset, out) that is activated in place and, in the backward sweep,
 // overwritten in place with the pre-activation gradients, which then feed ONE batched x-dgrad and the batched
 // weight gradients.
+//
+// Two ways of overlapping the sequential part: the whole-clip entry points split the batch into
+// independent chains on helper streams (SliceFork below); the frame-range entry points run frames [t0, t1) only, with
+// the sweep's state kept in the caller's workspace between calls, so that a caller can run the layers of a stack as a
+// wavefront, one stream per layer (ops.GRUStackFn).
 #include <cuda_bf16.h>
 
 #include "common.cuh"
