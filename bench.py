@@ -111,6 +111,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--force-port", action="store_true", help="reference arm: time the oracle port even if baseline/_ref exists")
     ap.add_argument("--cpu-frames", type=int, default=None, help="debug: shrink the CPU sample")
+    ap.add_argument("--cpu-clips", type=int, default=None,
+                    help="reference arm: clips per CPU step (default 2, or 1 when more than 12 steps are asked for)")
     ap.add_argument("--prof-dump", default=None, help="write the per-shape launch table of the timed steps here")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only (ncu launch list): skip the e2e leg")
     a = ap.parse_args()
@@ -167,7 +169,7 @@ def cpu_step_time(a, steps, warmup, frames=None):
     dt = (time.perf_counter() - t0) / steps
     sample = f"{steps} full G+Ds+Dt step(s) of {B} clip x {T}f x {side}x{side}, k={min(a.k_sample, T)}, " \
              f"{a.classes} classes, ch={a.ch}, fp32, {warmup} warm-up"
-    return B / dt, cores, sample, dt
+    return B / dt, cores, sample, dt, B
 
 
 REF_DIR = os.path.join(ROOT, "baseline", "_ref")          # git-ignored copy of /root/reference; travels with the snapshot
@@ -189,7 +191,10 @@ def ref_cpu_step_time(a, steps, warmup, frames=None):
     torch.nn.Module.cuda = lambda self, *aa, **kk: self
     torch.Tensor.cuda = lambda self, *aa, **kk: self
     import trainer as ref_trainer
-    T, B = frames or a.frames, 2
+    T = frames or a.frames
+    # clips per CPU step: 2 while K + 1 such steps (~13 s each on 16 cores) end within ~3 minutes, else 1 --
+    # the per-clip CPU cost is flat in B, so the clips/s figure does not depend on the choice
+    B = a.cpu_clips or (2 if steps + warmup <= 12 else 1)
     n = steps + warmup
     torch.manual_seed(0)
     clips = [torch.rand(B, 3, T, 64, 64) * 2 - 1 for _ in range(n)]
@@ -232,9 +237,9 @@ def ref_cpu_step_time(a, steps, warmup, frames=None):
         os.close(real_stdout)
     ends = [t_start] + marks[2::3]          # step boundaries (the optimizer step of G falls into the next interval)
     dt = (ends[-1] - ends[warmup]) / steps
-    sample = f"{steps} full G+Ds+Dt step(s) of the unmodified reference Trainer.train() (baseline/_ref), {B} clips x {T}f x " \
+    sample = f"{steps} full G+Ds+Dt step(s) of the unmodified reference Trainer.train() (baseline/_ref), {B} clip{'s' if B > 1 else ''} x {T}f x " \
              f"64x64, k={min(a.k_sample, T)}, {a.classes} classes, ch={a.ch}, fp32, {warmup} warm-up"
-    return B / dt, cores, sample, dt
+    return B / dt, cores, sample, dt, B
 
 
 def run_reference(a):
@@ -244,15 +249,15 @@ def run_reference(a):
     # warm-ups are full steps too (~10-25 s each on 8-16 cores); cap them so the run ends within minutes
     kind = "reference" if (os.path.isdir(REF_DIR) and a.latent_dim == 4 and not a.force_port) else "port"
     if kind == "reference":
-        v, cores, sample, dt = ref_cpu_step_time(a, a.steps, min(a.warmup, 1), a.cpu_frames)
+        v, cores, sample, dt, clips_per_step = ref_cpu_step_time(a, a.steps, min(a.warmup, 1), a.cpu_frames)
     else:
-        v, cores, sample, dt = cpu_step_time(a, a.steps, min(a.warmup, 1), a.cpu_frames)
+        v, cores, sample, dt, clips_per_step = cpu_step_time(a, a.steps, min(a.warmup, 1), a.cpu_frames)
     line = {
         "impl": "reference", "metric": metric_name(a), "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(a, a.batch, max(a.gpus, 1)) + "; CPU sample = "
-                               + ("2 clips" if kind == "reference" else "1 clip") + " per step",
+                               + ("1 clip" if clips_per_step == 1 else f"{clips_per_step} clips") + " per step",
                    "timing": "host wall clock"},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
